@@ -1,0 +1,1020 @@
+// b200rt.cu — sm_100a kernels and the C ABI of include/b200rt.h.
+//
+// Kernels (SURVEY.md §2 "new kernels"):
+//   K2 path_trace_kernel    render_scanline + ray_color     (render.rs:17-70)
+//   K1 closest_hit_kernel   BboxTree::hit_workspace batch   (bvh/bbox_tree.rs:56-91)
+//   K3 resolve_kernel       to_image + Color::to_pixel      (image.rs:34-40, core/color.rs:31-38)
+//   K4 scatter_kernel       MaterialType::scatter/emitted   (material_type.rs:50-79)
+//   + small parity hooks (aabb_hit, camera_rays, texture_value, rng) and an FFMA-chain
+//   microbenchmark that measures the FP32 issue ceiling used as the roofline denominator.
+// No tensor cores: nothing on this path is a dense contraction.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bvh_build.hpp"
+#include "rt_device.cuh"
+
+namespace b200rt {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CU(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, \
+                                           "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------
+constexpr int BLOCK = 256;          // threads per CTA (8 warps)
+constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
+
+struct SmemPlan {
+    uint32_t all_in_smem;           // 1: nodes + geom + mats + tex all staged (SmemAcc)
+    uint32_t n_top;                 // nodes staged when !all_in_smem
+    uint32_t stack_depth;           // entries per thread
+    uint32_t bytes;                 // dynamic shared memory per CTA
+};
+
+struct Counters {                   // device-side, one per in-flight render
+    unsigned long long rays, paths, nodes, prims, exhausted;
+    unsigned int tile_counter, pad;
+};
+
+struct RenderArgs {
+    DeviceScene scene;
+    DeviceCamera cam;
+    SmemPlan plan;
+    RngKeys keys;
+    uint32_t samples, sample_offset, max_depth;
+    uint32_t row_begin, row_end;
+    uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
+    uint32_t shard_count, shard_index;
+    uint32_t accumulate;
+    float4* accum;
+    Counters* counters;
+};
+
+// Stage the scene (or the top of the BVH) into shared memory and set up the accessor.
+// Shared layout: [nodes][geom][mats][tex][stack: stack_depth x BLOCK ints]
+template <class Acc> struct Stager;
+template <> struct Stager<SmemAcc> {
+    static __device__ __forceinline__ SmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
+        uint32_t n_nodes4 = s.n_nodes * 4, n_geom4 = s.n_prims * 2, n_mat4 = s.n_prims * 2, n_tex4 = s.n_tex * 2;
+        float4* nodes = smem;
+        float4* geom = nodes + n_nodes4;
+        float4* mats = geom + n_geom4;
+        float4* tex = mats + n_mat4;
+        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
+        const float4* gg = reinterpret_cast<const float4*>(s.geom);
+        const float4* gm = reinterpret_cast<const float4*>(s.mats);
+        const float4* gt = reinterpret_cast<const float4*>(s.tex);
+        for (uint32_t i = threadIdx.x; i < n_nodes4; i += blockDim.x) nodes[i] = __ldg(gn + i);
+        for (uint32_t i = threadIdx.x; i < n_geom4; i += blockDim.x) geom[i] = __ldg(gg + i);
+        for (uint32_t i = threadIdx.x; i < n_mat4; i += blockDim.x) mats[i] = __ldg(gm + i);
+        for (uint32_t i = threadIdx.x; i < n_tex4; i += blockDim.x) tex[i] = __ldg(gt + i);
+        *stack = reinterpret_cast<int*>(tex + n_tex4);
+        __syncthreads();
+        SmemAcc a; a.nodes = nodes; a.geom = geom; a.mats = mats; a.tex = tex;
+        return a;
+    }
+};
+template <> struct Stager<GmemAcc> {
+    static __device__ __forceinline__ GmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
+        uint32_t n_top4 = plan.n_top * 4;
+        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
+        for (uint32_t i = threadIdx.x; i < n_top4; i += blockDim.x) smem[i] = __ldg(gn + i);
+        *stack = reinterpret_cast<int*>(smem + n_top4);
+        __syncthreads();
+        GmemAcc a;
+        a.nodes = gn; a.geom = reinterpret_cast<const float4*>(s.geom);
+        a.mats = reinterpret_cast<const float4*>(s.mats); a.tex = reinterpret_cast<const float4*>(s.tex);
+        a.top = smem; a.n_top = (int)plan.n_top;
+        return a;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// K2: persistent path-tracing megakernel.
+// Grid = (#SMs x resident CTAs); each warp pulls 8x4-pixel tiles from a global counter
+// (bottom rows first: the geometry-heavy tiles are scheduled before the cheap sky tiles).
+// One lane owns one pixel and walks its samples in order with path regeneration: a lane
+// whose path ends starts its next sample at the top of the loop instead of idling until
+// the warp's longest path finishes, so every traversal round has as many live lanes as the
+// tile still has work for.  Per-pixel sums stay in registers and are written once
+// (render.rs:59,66,68), as float4 {r, g, b, n}.
+// ------------------------------------------------------------------------------------------
+template <class Acc, bool COUNT>
+__global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant__ RenderArgs a) {
+    extern __shared__ float4 smem[];
+    int* stack_base;
+    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
+    int* stack = stack_base + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
+
+    for (;;) {
+        unsigned int j = 0;
+        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
+        j = __shfl_sync(FULL, j, 0);
+        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
+        if (t64 >= a.n_tiles) break;
+        uint32_t t = (uint32_t)t64;
+        uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        uint32_t px = tx * TILE_W + (lane & (TILE_W - 1));
+        uint32_t py = (a.tile_row0 + ty) * TILE_H + (lane >> 3);
+        bool valid = px < a.cam.width && py >= a.row_begin && py < a.row_end;
+        uint32_t pix = py * a.cam.width + px;
+
+        float3 sum = f3(0.f, 0.f, 0.f);
+        uint32_t s = 0, nrays = 0, nexh = 0;
+        TravCounters tc; tc.nodes = 0; tc.prims = 0;
+        bool alive = false;
+        Rng rng; rng.state = 0; rng.inc = 1;
+        RayF ray = make_ray(f3(0, 0, 0), f3(0, 0, 1));
+        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
+        uint32_t depth = 0;
+
+        for (;;) {
+            if (!alive && valid && s < a.samples) {
+                // render_scanline body, render.rs:60-66
+                rng.init(a.keys, pix, a.sample_offset + s);
+                float jx = (float)px + rng.gen();
+                float jy = (float)py + rng.gen();
+                float3 o, d;
+                pixel_ray(a.cam, rng, jx, jy, &o, &d);
+                ray = make_ray(o, d);
+                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
+                depth = a.max_depth;
+                alive = depth > 0;
+                ++s;
+            }
+            if (!__any_sync(FULL, alive)) break;
+            if (alive) {
+                // one iteration of ray_color's loop, render.rs:30-46
+                Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+                closest_hit<COUNT>(ray, acc, stack, BLOCK, 0.001f, c, tc);
+                ++nrays;
+                bool done;
+                if (c.code < 0) {
+                    emit = emit + atten * background(a.scene, ray.d);
+                    done = true;
+                } else {
+                    HitRec h = make_hit(ray, acc, c);
+                    ShadeOut so = shade(a.scene, acc, ray, h, rng, atten, emit);
+                    done = !so.scattered;
+                    if (!done) {
+                        ray = make_ray(so.o, so.d);
+                        if (--depth == 0) { done = true; ++nexh; }
+                    }
+                }
+                if (done) { sum = sum + emit; alive = false; }
+            }
+        }
+        if (valid) {
+            float4* dst = a.accum + pix;
+            float4 v = make_float4(sum.x, sum.y, sum.z, (float)a.samples);
+            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+        w_rays += nrays; w_exh += nexh; w_paths += valid ? a.samples : 0;
+        if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
+    }
+    // one set of atomics per warp per kernel
+    for (int o = 16; o > 0; o >>= 1) {
+        w_rays += __shfl_down_sync(FULL, w_rays, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o);
+        w_exh += __shfl_down_sync(FULL, w_exh, o);
+        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->rays, w_rays);
+        atomicAdd(&a.counters->paths, w_paths);
+        atomicAdd(&a.counters->exhausted, w_exh);
+        if (COUNT) { atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: closest-hit over a ray array, one thread per ray (grid-stride).
+// ------------------------------------------------------------------------------------------
+struct HitArgs {
+    DeviceScene scene; SmemPlan plan;
+    const B200rtRay* rays; size_t n; float t_min, t_max;
+    int32_t* ids; B200rtHit* hits; Counters* counters;
+};
+
+template <class Acc, bool COUNT>
+__global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constant__ HitArgs a) {
+    extern __shared__ float4 smem[];
+    int* stack_base;
+    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
+    int* stack = stack_base + threadIdx.x;
+    TravCounters tc; tc.nodes = 0; tc.prims = 0;
+    unsigned long long nr = 0;
+    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BLOCK) {
+        B200rtRay in = a.rays[i];
+        RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
+        Closest c; c.t = a.t_max; c.code = -1; c.face = 0;
+        closest_hit<COUNT>(ray, acc, stack, BLOCK, a.t_min, c, tc);
+        ++nr;
+        int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_LEAF_ID_MASK);
+        a.ids[i] = id;
+        if (a.hits) {
+            B200rtHit out;
+            memset(&out, 0, sizeof out);
+            out.id = id;
+            if (id >= 0) {
+                HitRec h = make_hit(ray, acc, c);
+                float u, v;
+                hit_uv(h, acc, &u, &v);
+                out.t = h.t; out.p[0] = h.p.x; out.p[1] = h.p.y; out.p[2] = h.p.z;
+                out.n[0] = h.n.x; out.n[1] = h.n.y; out.n[2] = h.n.z;
+                out.u = u; out.v = v; out.front_face = h.front ? 1 : 0;
+            }
+            a.hits[i] = out;
+        }
+    }
+    if (a.counters) {
+        atomicAdd(&a.counters->rays, nr);
+        if (COUNT) { atomicAdd(&a.counters->nodes, (unsigned long long)tc.nodes); atomicAdd(&a.counters->prims, (unsigned long long)tc.prims); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: resolve.  to_image (image.rs:34-40): c * (1/samples), sqrt, (x * 255.999) as u8
+// (saturating, NaN -> 0), vertical flip.  Evaluated in f64 like the reference so the bytes
+// are bit-identical to the oracle's for the same accumulation buffer.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned char to_pixel(double x) {
+    double v = x * 255.999;
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (unsigned char)v;
+}
+__global__ void resolve_kernel(const float4* __restrict__ accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t j = blockIdx.y;
+    if (i >= W || j >= H) return;
+    float4 c = accum[(size_t)j * W + i];
+    double n = samples ? (double)samples : (double)c.w;
+    double inv = 1.0 / n;
+    uint8_t* px = out + ((size_t)(H - 1 - j) * W + i) * 3;
+    px[0] = to_pixel(sqrt((double)c.x * inv));
+    px[1] = to_pixel(sqrt((double)c.y * inv));
+    px[2] = to_pixel(sqrt((double)c.z * inv));
+}
+
+// ------------------------------------------------------------------------------------------
+// parity-hook kernels
+// ------------------------------------------------------------------------------------------
+__global__ void aabb_hit_kernel(const float* __restrict__ boxes6, const B200rtRay* __restrict__ rays, size_t n, float t_min, float t_max, uint8_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    B200rtRay in = rays[i];
+    RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
+    const float* b = boxes6 + i * 6;
+    float e;
+    out[i] = aabb_hit2(ray, b[0], b[1], b[2], b[3], b[4], b[5], t_min, t_max, &e) ? 1 : 0;
+}
+
+struct ScatterArgs { DeviceScene scene; const B200rtRay* rays; const B200rtHit* hits; size_t n; RngKeys keys; B200rtScatter* out; };
+__global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    GmemAcc acc;
+    acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
+    acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
+    acc.top = nullptr; acc.n_top = 0;
+    B200rtRay in = a.rays[i];
+    B200rtHit hi = a.hits[i];
+    B200rtScatter out; memset(&out, 0, sizeof out);
+    if (hi.id >= 0 && (uint32_t)hi.id < a.scene.n_prims) {
+        RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
+        // rebuild the device hit record from the caller's record; u,v come from the geometry
+        HitRec h;
+        h.id = hi.id; h.t = hi.t; h.p = f3(hi.p[0], hi.p[1], hi.p[2]); h.n = f3(hi.n[0], hi.n[1], hi.n[2]);
+        h.front = hi.front_face != 0;
+        h.n_out = h.front ? h.n : -h.n;
+        h.type = 0xffu; h.face = 0;
+        h.has_uv = true; h.uv_u = hi.u; h.uv_v = hi.v;   // Texture::value(record.u, record.v, ..), lambertian.rs:34
+        Rng rng; rng.init(a.keys, (uint32_t)i, 0u);
+        uint32_t s0 = rng.state;
+        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
+        ShadeOut so = shade(a.scene, acc, ray, h, rng, atten, emit);
+        out.ray.ox = so.o.x; out.ray.oy = so.o.y; out.ray.oz = so.o.z;
+        out.ray.dx = so.d.x; out.ray.dy = so.d.y; out.ray.dz = so.d.z;
+        out.attenuation[0] = atten.x; out.attenuation[1] = atten.y; out.attenuation[2] = atten.z;
+        out.emitted[0] = emit.x; out.emitted[1] = emit.y; out.emitted[2] = emit.z;
+        out.scattered = so.scattered ? 1 : 0;
+        // draws consumed = LCG steps between s0 and rng.state: recount by stepping
+        uint32_t st = s0, k = 0;
+        while (st != rng.state && k < 4096) { st = st * 747796405u + rng.inc; ++k; }
+        out.draws = k;
+    }
+    a.out[i] = out;
+}
+
+__global__ void camera_rays_kernel(DeviceCamera cam, const float* __restrict__ xy, size_t n, RngKeys keys, B200rtRay* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Rng rng; rng.init(keys, (uint32_t)i, 0u);
+    float3 o, d;
+    pixel_ray(cam, rng, xy[2 * i], xy[2 * i + 1], &o, &d);
+    B200rtRay r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+    out[i] = r;
+}
+
+struct TexArgs { DeviceScene scene; int32_t tex; const float* uvp5; size_t n; float* out; };
+__global__ void texture_value_kernel(const __grid_constant__ TexArgs a) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    GmemAcc acc;
+    acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
+    acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
+    acc.top = nullptr; acc.n_top = 0;
+    const float* q = a.uvp5 + i * 5;
+    HitRec h;
+    h.id = -1; h.type = 0xffu; h.face = 0; h.t = 0; h.front = true;
+    h.p = f3(q[2], q[3], q[4]); h.n = f3(0, 1, 0); h.n_out = h.n;
+    h.has_uv = true; h.uv_u = q[0]; h.uv_v = q[1];
+    float3 c = texture_value(acc, a.scene.images, a.scene.perlin, a.tex, h);
+    a.out[i * 3 + 0] = c.x; a.out[i * 3 + 1] = c.y; a.out[i * 3 + 2] = c.z;
+}
+
+__global__ void rng_kernel(RngKeys keys, uint32_t ka, uint32_t kb, size_t n, float* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Rng rng; rng.init(keys, ka, kb);
+        for (size_t i = 0; i < n; ++i) out[i] = rng.gen();
+    }
+}
+
+// FP32 issue ceiling: 8 independent FFMA chains per thread.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float b, float c) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fmaf(x0, b, c); x1 = fmaf(x1, b, c); x2 = fmaf(x2, b, c); x3 = fmaf(x3, b, c);
+            x4 = fmaf(x4, b, c); x5 = fmaf(x5, b, c); x6 = fmaf(x6, b, c); x7 = fmaf(x7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace b200rt
+
+// ==========================================================================================
+// host side of the C ABI
+// ==========================================================================================
+using namespace b200rt;
+
+namespace {
+
+struct Scratch {                     // per in-flight render: counters, events, staging
+    Counters* d_counters = nullptr;
+    Counters* h_counters = nullptr;  // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaStream_t own_stream = nullptr;
+    float4* d_accum = nullptr; size_t accum_px = 0;
+    uint8_t* d_rgb = nullptr; size_t rgb_bytes = 0;
+    uint32_t launches = 0;
+};
+
+}  // namespace
+
+struct B200rtScene {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    DeviceScene ds{};
+    B200rtSceneInfo info{};
+    std::vector<void*> allocs;
+    std::mutex mu;
+    std::vector<Scratch*> free_scratch;
+    std::map<void*, Scratch*> inflight;   // keyed by stream
+    uint32_t max_coord_bits = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1; bool ok = false;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int resolve_device(int device, int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(B200RT_ECUDA, "no CUDA device available (%s); this backend has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0) { CU(cudaGetDevice(&device)); }
+    if (device >= n) return fail(B200RT_EINVAL, "device %d out of range (%d visible)", device, n);
+    *out = device;
+    return B200RT_OK;
+}
+
+template <class T> int upload(B200rtScene* sc, const std::vector<T>& host, const T** dev) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+    CU(cudaMalloc(&p, bytes));
+    sc->allocs.push_back(p);
+    sc->info.device_bytes += bytes;
+    if (!host.empty()) CU(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = reinterpret_cast<const T*>(p);
+    return B200RT_OK;
+}
+
+int validate(const B200rtSceneDesc* d) {
+    if (!d) return fail(B200RT_EINVAL, "scene description is NULL");
+    if (d->abi_version != B200RT_ABI_VERSION) return fail(B200RT_EINVAL, "abi_version %u != %u", d->abi_version, B200RT_ABI_VERSION);
+    if (d->n_prims > B200RT_LEAF_ID_MASK) return fail(B200RT_EINVAL, "too many primitives (%u)", d->n_prims);
+    if (d->n_prims && (!d->prims || !d->materials)) return fail(B200RT_EINVAL, "prims/materials NULL");
+    if ((d->n_spheres && !d->spheres) || (d->n_rects && !d->rects) || (d->n_boxes && !d->boxes) || (d->n_textures && !d->textures) ||
+        (d->n_images && !d->images) || (d->n_perlin && !d->perlin))
+        return fail(B200RT_EINVAL, "array pointer NULL with non-zero count");
+    for (uint32_t i = 0; i < d->n_prims; ++i) {
+        const B200rtPrimRef& p = d->prims[i];
+        uint32_t lim = p.type == B200RT_PRIM_SPHERE ? d->n_spheres : (p.type == B200RT_PRIM_BOX ? d->n_boxes : (p.type <= B200RT_PRIM_RECT_XZ ? d->n_rects : 0));
+        if (p.type > B200RT_PRIM_BOX || p.index >= lim) return fail(B200RT_EINVAL, "prim %u: bad type/index (%u, %u)", i, p.type, p.index);
+        if (p.type >= B200RT_PRIM_RECT_XY && p.type <= B200RT_PRIM_RECT_XZ && d->rects[p.index].kind != p.type)
+            return fail(B200RT_EINVAL, "prim %u: rect kind %u does not match prim type %u", i, d->rects[p.index].kind, p.type);
+        const B200rtMaterial& m = d->materials[i];
+        if (m.kind > B200RT_MAT_FAIRY_LIGHT) return fail(B200RT_EINVAL, "prim %u: bad material kind %u", i, m.kind);
+        bool textured = m.kind == B200RT_MAT_LAMBERTIAN || m.kind == B200RT_MAT_DIFFUSE_LIGHT || m.kind == B200RT_MAT_FAIRY_LIGHT;
+        if (textured && (m.texture < 0 || (uint32_t)m.texture >= d->n_textures)) return fail(B200RT_EINVAL, "prim %u: texture index %d out of range", i, m.texture);
+    }
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const B200rtTexture& x = d->textures[t];
+        if (x.kind > B200RT_TEX_CHECKER) return fail(B200RT_EINVAL, "texture %u: bad kind %u", t, x.kind);
+        if (x.kind == B200RT_TEX_CHECKER && (x.odd < 0 || x.even < 0 || (uint32_t)x.odd >= t || (uint32_t)x.even >= t))
+            return fail(B200RT_EINVAL, "texture %u: checker children must reference lower indices", t);
+        if (x.kind == B200RT_TEX_IMAGE && (x.image < 0 || (uint32_t)x.image >= d->n_images)) return fail(B200RT_EINVAL, "texture %u: image index out of range", t);
+        if (x.kind == B200RT_TEX_PERLIN && (x.image < 0 || (uint32_t)x.image >= d->n_perlin)) return fail(B200RT_EINVAL, "texture %u: perlin index out of range", t);
+    }
+    for (uint32_t i = 0; i < d->n_images; ++i)
+        if (!d->images[i].rgb8 || d->images[i].width == 0 || d->images[i].height == 0) return fail(B200RT_EINVAL, "image %u: empty", i);
+    if (d->skybox.kind > B200RT_SKY_NONE) return fail(B200RT_EINVAL, "bad skybox kind %u", d->skybox.kind);
+    return B200RT_OK;
+}
+
+// shared-memory budget: stage everything when it fits, else the top of the BVH
+SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target) {
+    SmemPlan p{};
+    const DeviceScene& s = sc->ds;
+    size_t budget = sc->smem_optin / blocks_per_sm_target;
+    if (budget > sc->smem_optin) budget = sc->smem_optin;
+    budget = budget > 2048 ? budget - 1024 : budget;   // per-CTA reserved shared memory
+    p.stack_depth = s.bvh_depth + 2;
+    size_t stack_bytes = (size_t)p.stack_depth * BLOCK * sizeof(int);
+    size_t scene_bytes = (size_t)s.n_nodes * 64 + (size_t)s.n_prims * 64 + (size_t)s.n_tex * 32;
+    if (scene_bytes + stack_bytes <= budget) {
+        p.all_in_smem = 1; p.n_top = s.n_nodes;
+        p.bytes = (uint32_t)(scene_bytes + stack_bytes);
+    } else {
+        size_t room = budget > stack_bytes ? budget - stack_bytes : 0;
+        p.all_in_smem = 0;
+        p.n_top = (uint32_t)std::min<size_t>(s.n_nodes, room / 64);
+        p.bytes = (uint32_t)((size_t)p.n_top * 64 + stack_bytes);
+    }
+    return p;
+}
+
+DeviceCamera make_camera(const B200rtCamera& c) {
+    // camera/mod.rs:98-114 in f64, reduced to the constants the kernel needs
+    auto scale3 = [](const double* v, double s, double* o) { o[0] = v[0] * s; o[1] = v[1] * s; o[2] = v[2] * s; };
+    double horizontal[3], vertical[3], wf[3], ll[3];
+    scale3(c.u, c.width * c.focus_length, horizontal);
+    scale3(c.v, c.height * c.focus_length, vertical);
+    scale3(c.w, c.focal_length * c.focus_length, wf);
+    for (int k = 0; k < 3; ++k) ll[k] = c.origin[k] - horizontal[k] * 0.5 - vertical[k] * 0.5 - wf[k];
+    DeviceCamera d;
+    auto to3 = [](double x, double y, double z) { return make_float3((float)x, (float)y, (float)z); };
+    d.origin = to3(c.origin[0], c.origin[1], c.origin[2]);
+    d.llo = to3(ll[0] - c.origin[0], ll[1] - c.origin[1], ll[2] - c.origin[2]);
+    double W = (double)c.image_width, H = (double)c.image_height;
+    d.hw = to3(horizontal[0] / W, horizontal[1] / W, horizontal[2] / W);
+    d.vh = to3(vertical[0] / H, vertical[1] / H, vertical[2] / H);
+    double lr = c.lens_radius >= 0 ? c.lens_radius : 0.0;
+    d.ul = to3(c.u[0] * lr, c.u[1] * lr, c.u[2] * lr);
+    d.vl = to3(c.v[0] * lr, c.v[1] * lr, c.v[2] * lr);
+    d.width = c.image_width; d.height = c.image_height;
+    d.has_lens = c.lens_radius >= 0 ? 1 : 0;
+    return d;
+}
+
+int get_scratch(B200rtScene* sc, void* stream_key, Scratch** out) {
+    std::lock_guard<std::mutex> lk(sc->mu);
+    if (sc->inflight.count(stream_key)) return fail(B200RT_EINVAL, "a render is already in flight on this stream; call b200rt_render_device_finish first");
+    Scratch* s = nullptr;
+    if (!sc->free_scratch.empty()) { s = sc->free_scratch.back(); sc->free_scratch.pop_back(); }
+    else {
+        s = new Scratch();
+        cudaError_t e = cudaMalloc(&s->d_counters, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, sizeof(Counters));
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+        if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete s; return fail(B200RT_ECUDA, "scratch allocation: %s", cudaGetErrorString(e)); }
+    }
+    sc->inflight[stream_key] = s;
+    *out = s;
+    return B200RT_OK;
+}
+void put_scratch(B200rtScene* sc, void* stream_key) {
+    std::lock_guard<std::mutex> lk(sc->mu);
+    auto it = sc->inflight.find(stream_key);
+    if (it == sc->inflight.end()) return;
+    sc->free_scratch.push_back(it->second);
+    sc->inflight.erase(it);
+}
+
+template <class K> int set_smem(K kernel, uint32_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return B200RT_OK;
+}
+
+int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* d_accum, cudaStream_t stream, Scratch* scr) {
+    if (cam->image_width == 0 || cam->image_height == 0) return fail(B200RT_EINVAL, "camera image dimensions are zero");
+    if ((uint64_t)cam->image_width * cam->image_height > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "image too large");
+    RenderArgs a{};
+    a.scene = sc->ds;
+    a.cam = make_camera(*cam);
+    a.keys = rng_keys(prm->seed);
+    a.samples = prm->samples == 0 ? 1 : prm->samples;   // src/main.rs:75-80
+    a.sample_offset = prm->sample_offset;
+    a.max_depth = prm->max_depth;
+    uint32_t H = cam->image_height, W = cam->image_width;
+    a.row_begin = prm->row_begin; a.row_end = prm->row_end;
+    if (a.row_begin == 0 && a.row_end == 0) a.row_end = H;
+    if (a.row_end > H || a.row_begin > a.row_end) return fail(B200RT_EINVAL, "row range [%u,%u) outside image height %u", a.row_begin, a.row_end, H);
+    a.tiles_x = (W + TILE_W - 1) / TILE_W;
+    a.tile_row0 = a.row_begin / TILE_H;
+    uint32_t tile_row1 = (a.row_end + TILE_H - 1) / TILE_H;
+    a.n_tiles = a.tiles_x * (tile_row1 - a.tile_row0);
+    a.shard_count = prm->shard_count == 0 ? 1 : prm->shard_count;
+    a.shard_index = prm->shard_index;
+    if (a.shard_index >= a.shard_count) return fail(B200RT_EINVAL, "shard_index %u >= shard_count %u", a.shard_index, a.shard_count);
+    a.accumulate = (prm->flags & B200RT_FLAG_ACCUMULATE) ? 1 : 0;
+    a.accum = reinterpret_cast<float4*>(d_accum);
+    a.counters = scr->d_counters;
+    bool count = (prm->flags & B200RT_FLAG_COUNT_TRAVERSAL) != 0;
+
+    // occupancy: prefer 2 CTAs/SM when the staged scene allows it
+    SmemPlan plan = make_plan(sc, 2);
+    if (!plan.all_in_smem) { SmemPlan p1 = make_plan(sc, 1); if (p1.all_in_smem) plan = p1; }
+    a.plan = plan;
+
+    scr->launches = 0;
+    CU(cudaEventRecord(scr->ev0, stream));
+    CU(cudaMemsetAsync(scr->d_counters, 0, sizeof(Counters), stream));
+    if (!a.accumulate) CU(cudaMemsetAsync(d_accum, 0, (size_t)W * H * sizeof(float4), stream));
+    int blocks_per_sm = 0;
+    auto go = [&](auto kernel) -> int {
+        int rc = set_smem(kernel, plan.bytes); if (rc) return rc;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, BLOCK, plan.bytes));
+        if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path_trace_kernel does not fit on an SM (smem %u B)", plan.bytes);
+        uint32_t warps_needed = (a.n_tiles + a.shard_count - 1) / a.shard_count;
+        uint32_t grid = (uint32_t)(sc->sm_count * blocks_per_sm);
+        uint32_t grid_needed = (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32);
+        if (grid_needed < grid) grid = grid_needed ? grid_needed : 1;
+        CU(cudaEventRecord(scr->ev1, stream));
+        kernel<<<grid, BLOCK, plan.bytes, stream>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(scr->ev2, stream));
+        scr->launches += 1;
+        return B200RT_OK;
+    };
+    int rc;
+    if (plan.all_in_smem) rc = count ? go(path_trace_kernel<SmemAcc, true>) : go(path_trace_kernel<SmemAcc, false>);
+    else rc = count ? go(path_trace_kernel<GmemAcc, true>) : go(path_trace_kernel<GmemAcc, false>);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(scr->h_counters, scr->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    return B200RT_OK;
+}
+
+int finish_render(Scratch* scr, cudaStream_t stream, cudaEvent_t end_event, B200rtStats* stats) {
+    CU(cudaStreamSynchronize(stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->rays = scr->h_counters->rays; stats->paths = scr->h_counters->paths;
+        stats->node_visits = scr->h_counters->nodes; stats->prim_tests = scr->h_counters->prims;
+        stats->depth_exhausted = scr->h_counters->exhausted;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, scr->ev1, scr->ev2)); stats->kernel_ms = ms;
+        CU(cudaEventElapsedTime(&ms, scr->ev0, end_event)); stats->total_ms = ms;
+        stats->launches = scr->launches;
+    }
+    return B200RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200rt_last_error(void) { return g_last_error.c_str(); }
+int b200rt_abi_version(void) { return B200RT_ABI_VERSION; }
+int b200rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out) {
+    if (!out) return fail(B200RT_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = validate(d); if (rc) return rc;
+    rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", device);
+
+    std::vector<GeomRec> geom(d->n_prims);
+    std::vector<MatRec> mats(d->n_prims);
+    std::vector<BuildPrim> bprims;
+    bprims.reserve(d->n_prims);
+    float max_abs = 0.f;
+    for (uint32_t i = 0; i < d->n_prims; ++i) {
+        const B200rtPrimRef& p = d->prims[i];
+        GeomRec g{}; HostBox b{};
+        if (p.type == B200RT_PRIM_SPHERE) {
+            const B200rtSphere& s = d->spheres[p.index];
+            g.g0 = make_float4(s.cx, s.cy, s.cz, s.radius);
+            // sphere.rs:54-60: center -/+ (r,r,r); a negative radius yields an inverted box
+            b.lo[0] = s.cx - s.radius; b.lo[1] = s.cy - s.radius; b.lo[2] = s.cz - s.radius;
+            b.hi[0] = s.cx + s.radius; b.hi[1] = s.cy + s.radius; b.hi[2] = s.cz + s.radius;
+        } else if (p.type == B200RT_PRIM_BOX) {
+            const B200rtBox& x = d->boxes[p.index];
+            g.g0 = make_float4(x.min[0], x.min[1], x.min[2], 0.f);
+            g.g1 = make_float4(x.max[0], x.max[1], x.max[2], 0.f);
+            for (int k = 0; k < 3; ++k) { b.lo[k] = x.min[k]; b.hi[k] = x.max[k]; }   // rect.rs:158-163
+        } else {
+            const B200rtRect& r = d->rects[p.index];
+            g.g0 = make_float4(r.d1_min, r.d1_max, r.d2_min, r.d2_max);
+            g.g1 = make_float4(r.offset, 0.f, 0.f, 0.f);
+            int d1 = p.type == B200RT_PRIM_RECT_YZ ? 1 : 0, d2 = p.type == B200RT_PRIM_RECT_XY ? 1 : 2, dn = 3 - d1 - d2;
+            b.lo[d1] = r.d1_min; b.hi[d1] = r.d1_max; b.lo[d2] = r.d2_min; b.hi[d2] = r.d2_max;
+            b.lo[dn] = r.offset - 0.0001f; b.hi[dn] = r.offset + 0.0001f;             // rect.rs:9,82-99
+        }
+        geom[i] = g;
+        const B200rtMaterial& m = d->materials[i];
+        MatRec mr{};
+        mr.kind = m.kind; mr.tex = -1;
+        mr.m0 = make_float4(m.albedo[0], m.albedo[1], m.albedo[2], m.param);
+        if (m.kind == B200RT_MAT_METAL) mr.m0.w = m.param > 1.0f ? 1.0f : m.param;   // metal.rs:18-21
+        if (m.kind == B200RT_MAT_LAMBERTIAN || m.kind == B200RT_MAT_DIFFUSE_LIGHT || m.kind == B200RT_MAT_FAIRY_LIGHT) {
+            const B200rtTexture& t = d->textures[m.texture];
+            if (t.kind == B200RT_TEX_SOLID) mr.m0 = make_float4(t.rgb[0], t.rgb[1], t.rgb[2], 0.f);   // resolved at upload
+            else mr.tex = m.texture;
+        }
+        mats[i] = mr;
+        // the reference keeps inverted boxes in its tree, where Aabb::hit2 can never pass;
+        // here they simply get no leaf.  NaN boxes likewise.
+        bool valid = true;
+        for (int k = 0; k < 3; ++k) valid = valid && (b.lo[k] <= b.hi[k]);
+        if (!valid) continue;
+        BuildPrim bp; bp.box = b; bp.code = (int)((p.type << B200RT_LEAF_TYPE_SHIFT) | i);
+        for (int k = 0; k < 3; ++k) { bp.centroid[k] = 0.5f * (b.lo[k] + b.hi[k]); max_abs = std::max(max_abs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))); }
+        bprims.push_back(bp);
+    }
+    // Grow boxes by ~8 ulp of the scene's largest coordinate so the f32 slab test is
+    // conservative with respect to the f32 primitive tests (a box only culls).
+    float pad = max_abs * 1e-6f;
+    for (auto& bp : bprims) for (int k = 0; k < 3; ++k) { bp.box.lo[k] -= pad; bp.box.hi[k] += pad; }
+    BvhBuildResult bvh = build_bvh(std::move(bprims));
+    if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
+
+    std::vector<TexRec> tex(d->n_textures);
+    for (uint32_t t = 0; t < d->n_textures; ++t) {
+        const B200rtTexture& x = d->textures[t];
+        TexRec r{}; r.kind = x.kind; r.r = x.rgb[0]; r.g = x.rgb[1]; r.b = x.rgb[2]; r.scalar = x.scalar; r.odd = x.odd; r.even = x.even; r.image = x.image;
+        tex[t] = r;
+    }
+
+    B200rtScene* sc = new B200rtScene();
+    sc->device = device;
+    auto bail = [&](int code) { b200rt_scene_destroy(sc); return code; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(B200RT_ECUDA, "cudaGetDeviceProperties failed"));
+    sc->sm_count = prop.multiProcessorCount;
+    sc->smem_optin = prop.sharedMemPerBlockOptin;
+
+    static_assert(sizeof(HostNode) == sizeof(BvhNode), "node layout");
+    std::vector<BvhNode> nodes(bvh.nodes.size());
+    memcpy(nodes.data(), bvh.nodes.data(), nodes.size() * sizeof(BvhNode));
+    if ((rc = upload(sc, nodes, &sc->ds.nodes))) return bail(rc);
+    if ((rc = upload(sc, geom, &sc->ds.geom))) return bail(rc);
+    if ((rc = upload(sc, mats, &sc->ds.mats))) return bail(rc);
+    if ((rc = upload(sc, tex, &sc->ds.tex))) return bail(rc);
+    // images: RGB8 -> RGBA8 so a texel is one 4-byte load
+    std::vector<ImageRec> images(d->n_images);
+    for (uint32_t i = 0; i < d->n_images; ++i) {
+        const B200rtImage& im = d->images[i];
+        size_t n = (size_t)im.width * im.height;
+        std::vector<uchar4> rgba(n);
+        for (size_t k = 0; k < n; ++k) rgba[k] = make_uchar4(im.rgb8[3 * k], im.rgb8[3 * k + 1], im.rgb8[3 * k + 2], 255);
+        const uchar4* dp = nullptr;
+        if ((rc = upload(sc, rgba, &dp))) return bail(rc);
+        images[i].texels = dp; images[i].width = im.width; images[i].height = im.height; images[i].pad = 0;
+    }
+    if ((rc = upload(sc, images, &sc->ds.images))) return bail(rc);
+    std::vector<PerlinRec> perlin(d->n_perlin);
+    for (uint32_t i = 0; i < d->n_perlin; ++i) {
+        for (int k = 0; k < 256; ++k) perlin[i].ranfloat[k] = make_float4(d->perlin[i].ranfloat[k][0], d->perlin[i].ranfloat[k][1], d->perlin[i].ranfloat[k][2], 0.f);
+        memcpy(perlin[i].perm_x, d->perlin[i].perm_x, 256); memcpy(perlin[i].perm_y, d->perlin[i].perm_y, 256); memcpy(perlin[i].perm_z, d->perlin[i].perm_z, 256);
+    }
+    if ((rc = upload(sc, perlin, &sc->ds.perlin))) return bail(rc);
+    sc->ds.n_nodes = (uint32_t)nodes.size(); sc->ds.n_prims = d->n_prims; sc->ds.n_tex = d->n_textures; sc->ds.bvh_depth = bvh.depth;
+    sc->ds.sky_kind = d->skybox.kind == B200RT_SKY_ABOVE ? B200RT_SKY_ABOVE : B200RT_SKY_FLAT;
+    bool flat = d->skybox.kind == B200RT_SKY_FLAT;
+    sc->ds.sky_r = flat ? d->skybox.rgb[0] : 0.f; sc->ds.sky_g = flat ? d->skybox.rgb[1] : 0.f; sc->ds.sky_b = flat ? d->skybox.rgb[2] : 0.f;
+    sc->info.n_prims = d->n_prims; sc->info.n_bvh_nodes = sc->ds.n_nodes; sc->info.bvh_depth = bvh.depth;
+    SmemPlan plan = make_plan(sc, 2);
+    if (!plan.all_in_smem) { SmemPlan p1 = make_plan(sc, 1); if (p1.all_in_smem) plan = p1; }
+    sc->info.bvh_nodes_in_smem = plan.n_top;
+    *out = sc;
+    return B200RT_OK;
+}
+
+void b200rt_scene_destroy(B200rtScene* sc) {
+    if (!sc) return;
+    DeviceGuard guard(sc->device);
+    for (auto& kv : sc->inflight) sc->free_scratch.push_back(kv.second);
+    for (Scratch* s : sc->free_scratch) {
+        if (s->own_stream) { cudaStreamSynchronize(s->own_stream); cudaStreamDestroy(s->own_stream); }
+        cudaFree(s->d_counters); cudaFreeHost(s->h_counters);
+        if (s->ev0) cudaEventDestroy(s->ev0); if (s->ev1) cudaEventDestroy(s->ev1); if (s->ev2) cudaEventDestroy(s->ev2); if (s->ev3) cudaEventDestroy(s->ev3);
+        cudaFree(s->d_accum); cudaFree(s->d_rgb);
+        delete s;
+    }
+    for (void* p : sc->allocs) cudaFree(p);
+    delete sc;
+}
+
+int b200rt_scene_info(const B200rtScene* sc, B200rtSceneInfo* out) {
+    if (!sc || !out) return fail(B200RT_EINVAL, "NULL argument");
+    *out = sc->info;
+    return B200RT_OK;
+}
+
+int b200rt_render_device(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* d_accum, void* cuda_stream) {
+    if (!csc || !cam || !prm || !d_accum) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    DeviceGuard guard(sc->device);
+    Scratch* scr; int rc = get_scratch(sc, cuda_stream, &scr); if (rc) return rc;
+    rc = launch_render(sc, cam, prm, d_accum, (cudaStream_t)cuda_stream, scr);
+    if (rc) put_scratch(sc, cuda_stream);
+    return rc;
+}
+
+int b200rt_render_device_finish(const B200rtScene* csc, void* cuda_stream, B200rtStats* stats) {
+    if (!csc) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    DeviceGuard guard(sc->device);
+    Scratch* scr = nullptr;
+    { std::lock_guard<std::mutex> lk(sc->mu); auto it = sc->inflight.find(cuda_stream); if (it != sc->inflight.end()) scr = it->second; }
+    if (!scr) return fail(B200RT_EINVAL, "no render in flight on this stream");
+    int rc = finish_render(scr, (cudaStream_t)cuda_stream, scr->ev2, stats);
+    put_scratch(sc, cuda_stream);
+    return rc;
+}
+
+int b200rt_render(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* accum, B200rtStats* stats) {
+    if (!csc || !cam || !prm || !accum) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    int device = sc->device;
+    if (prm->device >= 0 && prm->device != device) return fail(B200RT_EINVAL, "params.device %d != scene device %d", prm->device, device);
+    DeviceGuard guard(device);
+    int key_local; void* key = &key_local;   // private key: concurrent host threads never collide
+    Scratch* scr; int rc = get_scratch(sc, key, &scr); if (rc) return rc;
+    size_t px = (size_t)cam->image_width * cam->image_height;
+    auto done = [&](int code) { put_scratch(sc, key); return code; };
+    if (scr->accum_px < px) {
+        cudaFree(scr->d_accum); scr->d_accum = nullptr; scr->accum_px = 0;
+        cudaError_t e = cudaMalloc(&scr->d_accum, px * sizeof(float4));
+        if (e != cudaSuccess) return done(fail(B200RT_ENOMEM, "accumulation buffer (%zu px): %s", px, cudaGetErrorString(e)));
+        scr->accum_px = px;
+    }
+    B200rtRenderParams p = *prm; p.flags &= ~B200RT_FLAG_ACCUMULATE;
+    rc = launch_render(sc, cam, &p, reinterpret_cast<float*>(scr->d_accum), scr->own_stream, scr);
+    if (rc) return done(rc);
+    cudaError_t e = cudaMemcpyAsync(accum, scr->d_accum, px * sizeof(float4), cudaMemcpyDeviceToHost, scr->own_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(scr->ev3, scr->own_stream);
+    if (e != cudaSuccess) return done(fail(B200RT_ECUDA, "D2H copy: %s", cudaGetErrorString(e)));
+    rc = finish_render(scr, scr->own_stream, scr->ev3, stats);
+    return done(rc);
+}
+
+int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream) {
+    if (!d_accum || !d_out || W == 0 || H == 0) return fail(B200RT_EINVAL, "bad argument");
+    dim3 block(128, 1), grid((W + 127) / 128, H);
+    resolve_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(reinterpret_cast<const float4*>(d_accum), W, H, samples, d_out);
+    CU(cudaGetLastError());
+    return B200RT_OK;
+}
+
+int b200rt_resolve_rgb8(const float* accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* out, int device) {
+    if (!accum || !out || W == 0 || H == 0) return fail(B200RT_EINVAL, "bad argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    size_t px = (size_t)W * H;
+    float* d_acc = nullptr; uint8_t* d_out = nullptr;
+    CU(cudaMalloc(&d_acc, px * 16));
+    cudaError_t e = cudaMalloc(&d_out, px * 3);
+    if (e != cudaSuccess) { cudaFree(d_acc); return fail(B200RT_ENOMEM, "resolve buffers: %s", cudaGetErrorString(e)); }
+    auto cleanup = [&]() { cudaFree(d_acc); cudaFree(d_out); };
+    e = cudaMemcpy(d_acc, accum, px * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { rc = b200rt_resolve_rgb8_device(d_acc, W, H, samples, d_out, nullptr); if (rc) { cleanup(); return rc; } }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, px * 3, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(B200RT_ECUDA, "resolve: %s", cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+}  // extern "C"
+
+// ---- parity hooks ---------------------------------------------------------------------------
+namespace {
+struct DevBuf {   // RAII device buffer for the hooks
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) { CU(cudaMalloc(&p, bytes ? bytes : 16)); return B200RT_OK; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+}  // namespace
+
+extern "C" {
+
+int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, float t_min, float t_max, int32_t* ids, B200rtHit* hits, B200rtStats* stats) {
+    if (!csc || (n && (!rays || !ids))) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    DeviceGuard guard(sc->device);
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return B200RT_OK;
+    DevBuf d_rays, d_ids, d_hits, d_ctr;
+    int rc;
+    if ((rc = d_rays.alloc(n * sizeof(B200rtRay))) || (rc = d_ids.alloc(n * sizeof(int32_t))) || (rc = d_ctr.alloc(sizeof(Counters)))) return rc;
+    if (hits && (rc = d_hits.alloc(n * sizeof(B200rtHit)))) return rc;
+    CU(cudaMemcpy(d_rays.p, rays, n * sizeof(B200rtRay), cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_ctr.p, 0, sizeof(Counters)));
+    HitArgs a{};
+    a.scene = sc->ds; a.rays = d_rays.as<B200rtRay>(); a.n = n; a.t_min = t_min; a.t_max = t_max;
+    a.ids = d_ids.as<int32_t>(); a.hits = hits ? d_hits.as<B200rtHit>() : nullptr; a.counters = d_ctr.as<Counters>();
+    SmemPlan plan = make_plan(sc, 2);
+    if (!plan.all_in_smem) { SmemPlan p1 = make_plan(sc, 1); if (p1.all_in_smem) plan = p1; }
+    a.plan = plan;
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    auto go = [&](auto kernel) -> int {
+        int r2 = set_smem(kernel, plan.bytes); if (r2) return r2;
+        int bps = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, BLOCK, plan.bytes));
+        if (bps < 1) return fail(B200RT_ECUDA, "closest_hit_kernel does not fit on an SM");
+        size_t want = (n + BLOCK - 1) / BLOCK;
+        uint32_t grid = (uint32_t)std::min<size_t>(want, (size_t)sc->sm_count * bps * 4);
+        CU(cudaEventRecord(e0));
+        kernel<<<grid, BLOCK, plan.bytes>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1));
+        return B200RT_OK;
+    };
+    if (plan.all_in_smem) rc = go(closest_hit_kernel<SmemAcc, true>); else rc = go(closest_hit_kernel<GmemAcc, true>);
+    if (rc == B200RT_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "closest_hit: %s", cudaGetErrorString(e));
+    }
+    if (rc == B200RT_OK) {
+        cudaMemcpy(ids, d_ids.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+        if (hits) cudaMemcpy(hits, d_hits.p, n * sizeof(B200rtHit), cudaMemcpyDeviceToHost);
+        if (stats) {
+            Counters c; cudaMemcpy(&c, d_ctr.p, sizeof c, cudaMemcpyDeviceToHost);
+            stats->rays = c.rays; stats->node_visits = c.nodes; stats->prim_tests = c.prims; stats->launches = 1;
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1); stats->kernel_ms = ms; stats->total_ms = ms;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "closest_hit copy-back: %s", cudaGetErrorString(e));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int b200rt_aabb_hit(const float* boxes6, const B200rtRay* rays, size_t n, float t_min, float t_max, uint8_t* out, int device) {
+    if (n && (!boxes6 || !rays || !out)) return fail(B200RT_EINVAL, "NULL argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    if (n == 0) return B200RT_OK;
+    DevBuf b, r, o;
+    if ((rc = b.alloc(n * 24)) || (rc = r.alloc(n * sizeof(B200rtRay))) || (rc = o.alloc(n))) return rc;
+    CU(cudaMemcpy(b.p, boxes6, n * 24, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.p, rays, n * sizeof(B200rtRay), cudaMemcpyHostToDevice));
+    aabb_hit_kernel<<<(unsigned)((n + 255) / 256), 256>>>(b.as<float>(), r.as<B200rtRay>(), n, t_min, t_max, o.as<uint8_t>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o.p, n, cudaMemcpyDeviceToHost));
+    return B200RT_OK;
+}
+
+int b200rt_scatter(const B200rtScene* csc, const B200rtRay* rays, const B200rtHit* hits, size_t n, uint64_t seed, B200rtScatter* out) {
+    if (!csc || (n && (!rays || !hits || !out))) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    DeviceGuard guard(sc->device);
+    if (n == 0) return B200RT_OK;
+    DevBuf r, h, o; int rc;
+    if ((rc = r.alloc(n * sizeof(B200rtRay))) || (rc = h.alloc(n * sizeof(B200rtHit))) || (rc = o.alloc(n * sizeof(B200rtScatter)))) return rc;
+    CU(cudaMemcpy(r.p, rays, n * sizeof(B200rtRay), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h.p, hits, n * sizeof(B200rtHit), cudaMemcpyHostToDevice));
+    ScatterArgs a{}; a.scene = sc->ds; a.rays = r.as<B200rtRay>(); a.hits = h.as<B200rtHit>(); a.n = n; a.keys = rng_keys(seed); a.out = o.as<B200rtScatter>();
+    scatter_kernel<<<(unsigned)((n + 127) / 128), 128>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o.p, n * sizeof(B200rtScatter), cudaMemcpyDeviceToHost));
+    return B200RT_OK;
+}
+
+int b200rt_camera_rays(const B200rtCamera* cam, const float* xy, size_t n, uint64_t seed, B200rtRay* out, int device) {
+    if (!cam || (n && (!xy || !out))) return fail(B200RT_EINVAL, "NULL argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    if (n == 0) return B200RT_OK;
+    DevBuf x, o;
+    if ((rc = x.alloc(n * 8)) || (rc = o.alloc(n * sizeof(B200rtRay)))) return rc;
+    CU(cudaMemcpy(x.p, xy, n * 8, cudaMemcpyHostToDevice));
+    camera_rays_kernel<<<(unsigned)((n + 255) / 256), 256>>>(make_camera(*cam), x.as<float>(), n, rng_keys(seed), o.as<B200rtRay>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o.p, n * sizeof(B200rtRay), cudaMemcpyDeviceToHost));
+    return B200RT_OK;
+}
+
+int b200rt_texture_value(const B200rtScene* csc, int32_t tex, const float* uvp5, size_t n, float* out_rgb) {
+    if (!csc || (n && (!uvp5 || !out_rgb))) return fail(B200RT_EINVAL, "NULL argument");
+    B200rtScene* sc = const_cast<B200rtScene*>(csc);
+    if (tex < 0 || (uint32_t)tex >= sc->ds.n_tex) return fail(B200RT_EINVAL, "texture index %d out of range", tex);
+    DeviceGuard guard(sc->device);
+    if (n == 0) return B200RT_OK;
+    DevBuf x, o; int rc;
+    if ((rc = x.alloc(n * 20)) || (rc = o.alloc(n * 12))) return rc;
+    CU(cudaMemcpy(x.p, uvp5, n * 20, cudaMemcpyHostToDevice));
+    TexArgs a{}; a.scene = sc->ds; a.tex = tex; a.uvp5 = x.as<float>(); a.n = n; a.out = o.as<float>();
+    texture_value_kernel<<<(unsigned)((n + 127) / 128), 128>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out_rgb, o.p, n * 12, cudaMemcpyDeviceToHost));
+    return B200RT_OK;
+}
+
+int b200rt_rng_uniforms(uint64_t seed, uint32_t ka, uint32_t kb, size_t n, float* out, int device) {
+    if (n && !out) return fail(B200RT_EINVAL, "NULL argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    if (n == 0) return B200RT_OK;
+    DevBuf o; if ((rc = o.alloc(n * 4))) return rc;
+    rng_kernel<<<1, 32>>>(rng_keys(seed), ka, kb, n, o.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+    return B200RT_OK;
+}
+
+int b200rt_fp32_peak(int device, double* lane_instr_per_s) {
+    if (!lane_instr_per_s) return fail(B200RT_EINVAL, "NULL argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    int grid = prop.multiProcessorCount * 8, iters = 4096;
+    DevBuf o; if ((rc = o.alloc((size_t)grid * 256 * 4))) return rc;
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fp32_peak_kernel<<<grid, 256>>>(o.as<float>(), iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(B200RT_ECUDA, "fp32_peak: %s", cudaGetErrorString(e)); }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        double ops = (double)grid * 256.0 * iters * 64.0;   // 8 chains x 8 unrolled FFMA per iteration
+        if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *lane_instr_per_s = best;
+    return B200RT_OK;
+}
+
+}  // extern "C"
