@@ -225,6 +225,14 @@ int  b200rt_scene_info(const B200rtScene* scene, B200rtSceneInfo* out);
 int  b200rt_render(const B200rtScene* scene, const B200rtCamera* camera,
                    const B200rtRenderParams* params, float* accum, B200rtStats* stats);
 
+/* render_scene's whole product (src/main.rs:85-128 minus the file write): render, then
+ * to_image's resolve (image.rs:34-40) on the device, then ONE device->host copy of the
+ * W*H*3 RGB8 bytes (top row first).  `accum` may be NULL; if not, the float4 sums are
+ * copied back as well. */
+int  b200rt_render_rgb8(const B200rtScene* scene, const B200rtCamera* camera,
+                        const B200rtRenderParams* params, uint8_t* out_rgb8, float* accum,
+                        B200rtStats* stats);
+
 /* Same, but `d_accum` is a DEVICE pointer (float4 per pixel) on the scene's device and the
  * work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) without
  * synchronising; stats (if not NULL) are filled by b200rt_render_device_finish. Lets a

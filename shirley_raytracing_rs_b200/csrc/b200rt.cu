@@ -636,6 +636,8 @@ int finish_render(Scratch* scr, cudaStream_t stream, cudaEvent_t end_event, B200
 
 extern "C" {
 
+int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream);
+
 const char* b200rt_last_error(void) { return g_last_error.c_str(); }
 int b200rt_abi_version(void) { return B200RT_ABI_VERSION; }
 int b200rt_device_count(void) {
@@ -802,8 +804,7 @@ int b200rt_render_device_finish(const B200rtScene* csc, void* cuda_stream, B200r
     return rc;
 }
 
-int b200rt_render(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* accum, B200rtStats* stats) {
-    if (!csc || !cam || !prm || !accum) return fail(B200RT_EINVAL, "NULL argument");
+static int render_host_impl(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* accum, uint8_t* out_rgb8, B200rtStats* stats) {
     B200rtScene* sc = const_cast<B200rtScene*>(csc);
     int device = sc->device;
     if (prm->device >= 0 && prm->device != device) return fail(B200RT_EINVAL, "params.device %d != scene device %d", prm->device, device);
@@ -818,14 +819,37 @@ int b200rt_render(const B200rtScene* csc, const B200rtCamera* cam, const B200rtR
         if (e != cudaSuccess) return done(fail(B200RT_ENOMEM, "accumulation buffer (%zu px): %s", px, cudaGetErrorString(e)));
         scr->accum_px = px;
     }
+    if (out_rgb8 && scr->rgb_bytes < px * 3) {
+        cudaFree(scr->d_rgb); scr->d_rgb = nullptr; scr->rgb_bytes = 0;
+        cudaError_t e = cudaMalloc(&scr->d_rgb, px * 3);
+        if (e != cudaSuccess) return done(fail(B200RT_ENOMEM, "rgb8 buffer: %s", cudaGetErrorString(e)));
+        scr->rgb_bytes = px * 3;
+    }
     B200rtRenderParams p = *prm; p.flags &= ~B200RT_FLAG_ACCUMULATE;
     rc = launch_render(sc, cam, &p, reinterpret_cast<float*>(scr->d_accum), scr->own_stream, scr);
     if (rc) return done(rc);
-    cudaError_t e = cudaMemcpyAsync(accum, scr->d_accum, px * sizeof(float4), cudaMemcpyDeviceToHost, scr->own_stream);
+    cudaError_t e = cudaSuccess;
+    if (out_rgb8) {
+        rc = b200rt_resolve_rgb8_device(reinterpret_cast<float*>(scr->d_accum), cam->image_width, cam->image_height, p.samples == 0 ? 1 : p.samples, scr->d_rgb, scr->own_stream);
+        if (rc) return done(rc);
+        scr->launches += 1;
+        e = cudaMemcpyAsync(out_rgb8, scr->d_rgb, px * 3, cudaMemcpyDeviceToHost, scr->own_stream);
+    }
+    if (e == cudaSuccess && accum) e = cudaMemcpyAsync(accum, scr->d_accum, px * sizeof(float4), cudaMemcpyDeviceToHost, scr->own_stream);
     if (e == cudaSuccess) e = cudaEventRecord(scr->ev3, scr->own_stream);
     if (e != cudaSuccess) return done(fail(B200RT_ECUDA, "D2H copy: %s", cudaGetErrorString(e)));
     rc = finish_render(scr, scr->own_stream, scr->ev3, stats);
     return done(rc);
+}
+
+int b200rt_render(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, float* accum, B200rtStats* stats) {
+    if (!csc || !cam || !prm || !accum) return fail(B200RT_EINVAL, "NULL argument");
+    return render_host_impl(csc, cam, prm, accum, nullptr, stats);
+}
+
+int b200rt_render_rgb8(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, uint8_t* out_rgb8, float* accum, B200rtStats* stats) {
+    if (!csc || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
+    return render_host_impl(csc, cam, prm, accum, out_rgb8, stats);
 }
 
 int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream) {

@@ -118,15 +118,12 @@ int b200rt_host_render_scene(const B200rtHostScene* sc, const B200rtCamera* cam,
     int rc = b200rt_scene_create(&sc->flat->desc, device, &dev);
     if (rc) return host_fail(rc, b200rt_last_error());
     size_t px = (size_t)cam->image_width * cam->image_height;
-    std::vector<float> accum(px * 4);
     B200rtRenderParams p{};
     p.samples = samples; p.max_depth = max_depth; p.seed = seed; p.device = -1;
-    rc = b200rt_render(dev, cam, &p, accum.data(), stats);
-    if (rc) { std::string m = b200rt_last_error(); b200rt_scene_destroy(dev); return host_fail(rc, m); }
     std::vector<uint8_t> rgb;
     uint8_t* dst = rgb8_out;
     if (!dst) { rgb.resize(px * 3); dst = rgb.data(); }
-    rc = b200rt_resolve_rgb8(accum.data(), cam->image_width, cam->image_height, samples == 0 ? 1 : samples, dst, device);   // image.samples = samples, main.rs:86
+    rc = b200rt_render_rgb8(dev, cam, &p, dst, nullptr, stats);   // image.samples = samples, main.rs:86
     if (rc) { std::string m = b200rt_last_error(); b200rt_scene_destroy(dev); return host_fail(rc, m); }
     b200rt_scene_destroy(dev);
     if (output_png) {
