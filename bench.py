@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (BASELINE: 500)")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--ref-spp", type=int, default=2, help="spp of the bounded CPU sample per step")
-    ap.add_argument("--cpu-baseline-spp", type=int, default=4)
+    ap.add_argument("--cpu-baseline-spp", type=int, default=128, help="bounded CPU sample: ~10-30 s of host work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
