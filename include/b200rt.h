@@ -173,6 +173,8 @@ typedef struct B200rtStats {
     double   total_ms;          /* device time incl. copies issued by this call                */
     uint32_t launches;          /* kernels launched by this call                               */
     uint32_t _pad;
+    uint64_t diag[8];           /* kernel-version specific lane-utilisation counters (COUNT_TRAVERSAL
+                                   only); not part of the parity contract          */
 } B200rtStats;
 
 typedef struct B200rtSceneInfo {

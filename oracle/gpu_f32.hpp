@@ -10,7 +10,7 @@
 // (SURVEY.md §8c check 1: "GPU vs oracle<float> bit-exact on the full fixed ray set").
 // The algorithm being restated is the reference's Sphere::hit / Rect::hit / RectBox::hit
 // (geometry/sphere.rs:29-52, geometry/rect.rs:55-80,147-156) with the quadratic solved in
-// its cancellation-free form.
+// its cancellation-free form and the box taken through its three slabs.
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -81,15 +81,24 @@ inline void hit_rect(const Ray32& r, const B200rtRect& g, uint32_t type, int id,
     if (accept_t(t, t_min, c, id)) { c.t = t; c.id = id; c.type = type; }
 }
 inline void hit_box(const Ray32& r, const B200rtBox& g, int id, float t_min, Closest32& c) {
-    float best = c.t; int face = -1; float t;
+    // RectBox::hit (rect.rs:147-156) through its three slabs: entry point if inside
+    // [t_min, closest], else exit point; axis priority y > x > z at equal t ("later face
+    // replaces", rect.rs:149-154).
     const float* lo = g.min; const float* hi = g.max;
-    t = rect_t(r, 0, 1, lo[0], hi[0], lo[1], hi[1], hi[2], t_min, best); if (t <= best) { best = t; face = 0; }
-    t = rect_t(r, 0, 1, lo[0], hi[0], lo[1], hi[1], lo[2], t_min, best); if (t <= best) { best = t; face = 1; }
-    t = rect_t(r, 1, 2, lo[1], hi[1], lo[2], hi[2], hi[0], t_min, best); if (t <= best) { best = t; face = 2; }
-    t = rect_t(r, 1, 2, lo[1], hi[1], lo[2], hi[2], lo[0], t_min, best); if (t <= best) { best = t; face = 3; }
-    t = rect_t(r, 0, 2, lo[0], hi[0], lo[2], hi[2], hi[1], t_min, best); if (t <= best) { best = t; face = 4; }
-    t = rect_t(r, 0, 2, lo[0], hi[0], lo[2], hi[2], lo[1], t_min, best); if (t <= best) { best = t; face = 5; }
-    if (face >= 0 && accept_t(best, t_min, c, id)) { c.t = best; c.id = id; c.type = B200RT_PRIM_BOX; c.face = face; }
+    float ax = (lo[0] - r.ox) * r.ix, bx = (hi[0] - r.ox) * r.ix;
+    float ay = (lo[1] - r.oy) * r.iy, by = (hi[1] - r.oy) * r.iy;
+    float az = (lo[2] - r.oz) * r.iz, bz = (hi[2] - r.oz) * r.iz;
+    float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+    float ny = fminf(ay, by), fy = fmaxf(ay, by);
+    float nz = fminf(az, bz), fz = fmaxf(az, bz);
+    float t_enter = fmaxf(fmaxf(nx, ny), nz), t_exit = fminf(fminf(fx, fy), fz);
+    if (!(t_enter <= t_exit)) return;
+    bool entering = t_enter >= t_min;
+    float t = entering ? t_enter : t_exit;
+    if (!accept_t(t, t_min, c, id)) return;
+    float ty = entering ? ny : fy, tx = entering ? nx : fx;
+    c.t = t; c.id = id; c.type = B200RT_PRIM_BOX;
+    c.face = (ty == t) ? 4 : ((tx == t) ? 2 : 0);
 }
 
 // Linear closest hit over every object in id order; fills `out` like the device make_hit.

@@ -89,7 +89,7 @@ class RenderParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("depth_exhausted", C.c_uint64), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("launches", C.c_uint32), ("_pad", C.c_uint32)]
+                ("launches", C.c_uint32), ("_pad", C.c_uint32), ("diag", C.c_uint64 * 8)]
 
 
 class SceneInfo(C.Structure):

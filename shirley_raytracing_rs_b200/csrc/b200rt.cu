@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -58,6 +59,7 @@ struct SmemPlan {
 struct Counters {                   // device-side, one per in-flight render
     unsigned long long rays, paths, nodes, prims, exhausted;
     unsigned int tile_counter, pad;
+    unsigned long long diag[8];
 };
 
 struct RenderArgs {
@@ -70,9 +72,18 @@ struct RenderArgs {
     uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
     uint32_t shard_count, shard_index;
     uint32_t accumulate;
+    uint32_t trav_threshold;                    // v2: leave the traversal loop when fewer lanes than this still traverse
+    uint32_t wf_inner, wf_fetch, wf_park;       // v3 thresholds (see path_trace_kernel_v3)
     float4* accum;
     Counters* counters;
 };
+
+__device__ __forceinline__ TopPrims top_of(const DeviceScene& s) {
+    TopPrims t; t.n = s.n_top_prims;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t.code[k] = s.top_prims[k];
+    return t;
+}
 
 // Stage the scene (or the top of the BVH) into shared memory and set up the accessor.
 // Shared layout: [nodes][geom][mats][tex][stack: stack_depth x BLOCK ints]
@@ -131,6 +142,7 @@ __global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant
     int* stack = stack_base + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
+    const TopPrims top = top_of(a.scene);
 
     unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
 
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant
             if (alive) {
                 // one iteration of ray_color's loop, render.rs:30-46
                 Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
-                closest_hit<COUNT>(ray, acc, stack, BLOCK, 0.001f, c, tc);
+                closest_hit<COUNT>(ray, acc, top, stack, BLOCK, 0.001f, c, tc);
                 ++nrays;
                 bool done;
                 if (c.code < 0) {
@@ -216,6 +228,546 @@ __global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant
     }
 }
 
+// Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
+// result does not depend on which lane traced which sample, nor on scheduling or sharding.
+__device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v) {
+    // 2^-32 fixed point; non-finite contributions are dropped (a NaN sample would blacken the
+    // reference's pixel; here it contributes nothing)
+    const float S = 4294967296.0f;
+    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (v2): the same persistent kernel restructured for SIMT efficiency (ncu on v1: 8.1 of 32
+// lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble
+// texture at 2.7):
+//  * while-while traversal: every lane runs inner-node visits until it holds a leaf, then the
+//    warp tests the postponed leaves together;
+//  * the traversal cursor is resumable, and the warp leaves the traversal loop as soon as
+//    fewer than `trav_threshold` lanes are still traversing: finished lanes shade, scatter and
+//    start their next segment (or next sample) instead of idling until the slowest lane ends;
+//  * scene-spanning primitives are tested up front, uniformly (DeviceScene::top_prims);
+//  * the Perlin marble is evaluated by the whole warp (coop_turbulence);
+//  * one-FMA slab planes against padded boxes (FAST).
+// ------------------------------------------------------------------------------------------
+template <class Acc, bool COUNT, bool FAST, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_constant__ RenderArgs a) {
+    extern __shared__ float4 smem[];
+    int* stack_base;
+    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
+    int* stack = stack_base + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    // per-warp fixed-point accumulators [32 pixels][3] behind the stack columns
+    long long* wacc = reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (threadIdx.x >> 5) * 96;
+    const TopPrims top = top_of(a.scene);
+    const float T_MIN = 0.001f;                      // render.rs:31
+    const bool has_perlin = a.scene.perlin != nullptr;
+
+    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
+    // lane-utilisation diagnostics (COUNT only, lane 0 of each warp):
+    //  d0 outer iterations, d1 sum of alive lanes, d2 sum of lanes with no samples left,
+    //  d3 traversal rounds, d4 sum of traversing lanes per round, d5 sum of lanes shaded,
+    //  d6 sum of lanes regenerated, d7 inner-node visit steps (warp-level)
+    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+
+    for (;;) {
+        unsigned int j = 0;
+        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
+        j = __shfl_sync(FULL, j, 0);
+        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
+        if (t64 >= a.n_tiles) break;
+        uint32_t t = (uint32_t)t64;
+        uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
+        const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
+        const bool valid = my_px < a.cam.width && my_py >= a.row_begin && my_py < a.row_end;
+        // The tile's work list: item i = sample * nv + k (k-th valid pixel).  Any lane takes the
+        // next item when its path ends, so all lanes stay busy until the tile is finished
+        // (with lane = pixel, 17 % of the lanes sat out of samples at tile ends).
+        const unsigned valid_mask = __ballot_sync(FULL, valid);
+        const uint32_t nv = (uint32_t)__popc(valid_mask);
+        const uint32_t n_items = a.samples * nv;
+        uint32_t next_item = 0;
+        for (int k = lane; k < 96; k += 32) wacc[k] = 0;
+        __syncwarp();
+        uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
+        uint32_t nrays = 0, nexh = 0, npaths = 0;
+        TravCounters tc; tc.nodes = 0; tc.prims = 0;
+        bool alive = false;
+        Rng rng; rng.state = 0; rng.inc = 1;
+        RayF ray = make_ray(f3(0, 0, 0), f3(0, 0, 1));
+        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
+        uint32_t depth = 0;
+        int node = B200RT_TRAV_DONE, sp = 0;
+        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+
+        for (;;) {
+            // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
+            unsigned want_m = __ballot_sync(FULL, !alive);
+            uint32_t item = next_item + (uint32_t)__popc(want_m & lt);
+            bool regen = !alive && item < n_items;
+            next_item = min(n_items, next_item + (uint32_t)__popc(want_m));
+            if (COUNT) { d0 += 1; d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
+            if (regen) {
+                uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
+                uint32_t kth = item - sidx * nv;
+                pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
+                uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
+                rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                float jx = (float)px + rng.gen();
+                float jy = (float)py + rng.gen();
+                float3 o, d;
+                pixel_ray(a.cam, rng, jx, jy, &o, &d);
+                ray = FAST ? make_ray_fast(o, d) : make_ray(o, d);
+                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
+                depth = a.max_depth;
+                alive = depth > 0;
+                ++npaths;
+                if (alive) {                          // first segment
+                    c.t = INFINITY; c.code = -1; c.face = 0;
+                    hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc);
+                    node = 0; sp = 0; ++nrays;
+                }
+            }
+            if (!__any_sync(FULL, alive)) break;
+            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
+
+            // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
+            for (;;) {
+                if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
+                while (node >= 0 && node != B200RT_TRAV_DONE) {
+                    if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
+                    trav_inner<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                }
+                if (node < 0) trav_leaf<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
+                if ((uint32_t)__popc(still) < a.trav_threshold) break;
+            }
+
+            // ---- shade the lanes whose traversal finished: ray_color's loop body, render.rs:31-46 ----
+            bool fin = alive && node == B200RT_TRAV_DONE;
+            if (COUNT) d5 += __popc(__ballot_sync(FULL, fin));
+            bool hit = fin && c.code >= 0;
+            bool done = false;
+            HitRec h;
+            ShadePrep sp_;
+            sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
+            h.p = f3(0.f, 0.f, 0.f);
+            if (fin && !hit) {
+                emit = emit + atten * background(a.scene, ray.d);
+                done = true;
+            }
+            if (hit) {
+                h = make_hit(ray, acc, c);
+                sp_ = shade_prepare(a.scene, acc, h);
+            }
+            float turb = 0.0f;
+            if (has_perlin) turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+            if (hit) {
+                float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
+                ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
+                done = !so.scattered;
+                if (!done) {
+                    if (--depth == 0) { done = true; ++nexh; }
+                    else {
+                        ray = FAST ? make_ray_fast(so.o, so.d) : make_ray(so.o, so.d);
+                        c.t = INFINITY; c.code = -1; c.face = 0;
+                        hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc);
+                        node = 0; sp = 0; ++nrays;
+                    }
+                }
+            }
+            if (done) { acc_add(wacc, pl, emit); alive = false; node = B200RT_TRAV_DONE; }
+        }
+        __syncwarp();
+        if (valid) {
+            const float inv = 1.0f / 4294967296.0f;
+            float4* dst = a.accum + (my_py * a.cam.width + my_px);
+            float4 v = make_float4((float)wacc[lane * 3 + 0] * inv, (float)wacc[lane * 3 + 1] * inv, (float)wacc[lane * 3 + 2] * inv, (float)a.samples);
+            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+        __syncwarp();
+        w_rays += nrays; w_exh += nexh; w_paths += npaths;
+        if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        w_rays += __shfl_down_sync(FULL, w_rays, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o);
+        w_exh += __shfl_down_sync(FULL, w_exh, o);
+        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->rays, w_rays);
+        atomicAdd(&a.counters->paths, w_paths);
+        atomicAdd(&a.counters->exhausted, w_exh);
+        if (COUNT) { atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims); }
+    }
+    if (COUNT) {
+        // d7 was counted by whichever lane led each divergent step: sum it over the warp
+        for (int o = 16; o > 0; o >>= 1) d7 += __shfl_down_sync(FULL, d7, o);
+        if (lane == 0) {
+            atomicAdd(&a.counters->diag[0], d0); atomicAdd(&a.counters->diag[1], d1); atomicAdd(&a.counters->diag[2], d2); atomicAdd(&a.counters->diag[3], d3);
+            atomicAdd(&a.counters->diag[4], d4); atomicAdd(&a.counters->diag[5], d5); atomicAdd(&a.counters->diag[6], d6); atomicAdd(&a.counters->diag[7], d7);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (v3): warp-level wavefront over a shared-memory path pool.
+//
+// Measured on v2 (scripts/diag.py): 26 lanes traverse per round but only 12.6 run each
+// inner-node step (lanes differ in how many nodes they visit), 17 % of the lanes sit out of
+// samples at the end of a tile, and shading batches hold ~21 lanes of mixed materials.  A
+// lane-owns-a-pixel design can only trade traversal efficiency against shading efficiency, so
+// here lanes are decoupled from paths:
+//   * every warp owns a pool of P path slots in shared memory (SoA: ray, attenuation, RNG,
+//     depth, hit) and the (pixel, sample) work list of its 8x4 tile;
+//   * GENERATE, TRAVERSE and SHADE run as warp-wide batches over slots picked with
+//     __ballot_sync/__popc compaction, so each phase runs on (up to) 32 live lanes;
+//   * in TRAVERSE a lane that finishes stores its hit and immediately claims the next waiting
+//     slot; when the queue is dry and only stragglers run, they are parked (cursor stays in
+//     registers) while the warp shades / generates, and resume afterwards;
+//   * per-pixel sums are 64-bit fixed point (2^-32) in shared memory: integer adds commute, so
+//     the image stays bit-deterministic and independent of scheduling and tile sharding.
+// ------------------------------------------------------------------------------------------
+// Slot states.  A finished traversal parks its slot under the shading KIND it needs, so
+// SHADE batches can be claimed one material at a time (no divergence inside a batch).
+enum { SLOT_EMPTY = 0, SLOT_TRAV = 1, SLOT_RUN = 2, SLOT_SHADE0 = 3 };
+enum { SK_MISS = 0, SK_METAL = 1, SK_DIELECTRIC = 2, SK_LAMBERT_SOLID = 3, SK_OTHER = 4, SK_COUNT = 5 };
+constexpr int POOL_FIELDS = 15;
+__host__ __device__ constexpr int pool_words(int P) { return 192 + 32 + POOL_FIELDS * P; }
+
+template <int P> struct Pool {
+    long long* acc;          // [32 pixels][3] fixed-point sums
+    int* list;               // [32] compaction scratch
+    float *ox, *oy, *oz, *dx, *dy, *dz, *ax, *ay, *az, *t;
+    int* code;
+    uint32_t *rs, *ri, *meta, *state;   // meta: pixel (5) | box face (3) << 5 | depth << 8
+    __device__ __forceinline__ explicit Pool(uint32_t* base) {
+        acc = reinterpret_cast<long long*>(base);
+        list = reinterpret_cast<int*>(base + 192);
+        float* f = reinterpret_cast<float*>(base + 224);
+        ox = f; oy = f + P; oz = f + 2 * P; dx = f + 3 * P; dy = f + 4 * P; dz = f + 5 * P;
+        ax = f + 6 * P; ay = f + 7 * P; az = f + 8 * P; t = f + 9 * P;
+        code = reinterpret_cast<int*>(f + 10 * P);
+        rs = reinterpret_cast<uint32_t*>(f + 11 * P); ri = rs + P; meta = rs + 2 * P; state = rs + 3 * P;
+    }
+};
+
+// Compaction: the lanes flagged `want` receive distinct slots currently in `state_wanted`,
+// lowest slot first; -1 when the pool has no more.  Returns how many such slots exist in *total.
+// Out of line (it is called from every phase) and scalar in/out only, so the call costs no
+// local-memory traffic: returns (slot & 0xffff) | (total << 16), slot 0xffff = none.
+template <int P>
+__device__ __noinline__ uint32_t claim_slots_packed(const uint32_t* state, int* list, uint32_t state_wanted, bool want) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < P / 32; ++k) {
+        bool is = state[k * 32 + lane] == state_wanted;
+        unsigned m = __ballot_sync(FULL, is);
+        int rank = n + __popc(m & lt);
+        if (is && rank < 32) list[rank] = k * 32 + lane;
+        n += __popc(m);
+    }
+    __syncwarp();
+    unsigned wm = __ballot_sync(FULL, want);
+    int j = __popc(wm & lt);
+    uint32_t slot = (want && j < n) ? (uint32_t)list[j] : 0xffffu;
+    __syncwarp();
+    return slot | ((uint32_t)n << 16);
+}
+template <int P>
+__device__ __forceinline__ int claim_slots(const Pool<P>& pool, uint32_t state_wanted, bool want, int lane, int* total) {
+    uint32_t r = claim_slots_packed<P>(pool.state, pool.list, state_wanted, want);
+    *total = (int)(r >> 16);
+    uint32_t slot = r & 0xffffu;
+    return slot == 0xffffu ? -1 : (int)slot;
+}
+
+// Store a freshly produced ray (camera ray or scattered ray) into its slot, after testing it
+// against the scene-spanning primitives: that test runs here, in a full uniform batch.
+template <bool COUNT, int P, class Acc>
+__device__ __forceinline__ void produce_ray(const Pool<P>& pool, int slot, const Acc& acc, const TopPrims& top, float3 o, float3 d, float3 atten,
+                                            const Rng& rng, uint32_t pixel, uint32_t depth, TravCounters& tc) {
+    RayF r = make_ray_shade(o, d);
+    Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+    hit_top_prims<COUNT>(r, acc, top, 0.001f, c, tc);
+    pool.ox[slot] = o.x; pool.oy[slot] = o.y; pool.oz[slot] = o.z;
+    pool.dx[slot] = d.x; pool.dy[slot] = d.y; pool.dz[slot] = d.z;
+    pool.ax[slot] = atten.x; pool.ay[slot] = atten.y; pool.az[slot] = atten.z;
+    pool.rs[slot] = rng.state; pool.ri[slot] = rng.inc;
+    pool.t[slot] = c.t; pool.code[slot] = c.code;
+    pool.meta[slot] = pixel | ((uint32_t)c.face << 5) | (depth << 8);
+    pool.state[slot] = SLOT_TRAV;
+}
+
+template <class Acc, bool COUNT, bool FAST, int BLK, int P>
+__global__ void __launch_bounds__(BLK, 1) path_trace_kernel_v3(const __grid_constant__ RenderArgs a) {
+    extern __shared__ float4 smem[];
+    int* stack_base;
+    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
+    int* stack = stack_base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    Pool<P> pool(reinterpret_cast<uint32_t*>(stack_base + a.plan.stack_depth * BLK) + warp * pool_words(P));
+    const TopPrims top = top_of(a.scene);
+    const float T_MIN = 0.001f;                      // render.rs:31
+    const bool has_perlin = a.scene.perlin != nullptr;
+    const int T_INNER = (int)a.wf_inner, F_FETCH = (int)a.wf_fetch, T_PARK = (int)a.wf_park;
+
+    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
+    // diagnostics (COUNT): d0 policy iterations, d1 shade batches, d2 kinds per shade batch,
+    // d3 inner warp-steps, d4 lanes in inner steps, d5 lanes shaded, d6 lanes generated, d7 fetch batches
+    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+    TravCounters tc; tc.nodes = 0; tc.prims = 0;
+
+    for (;;) {
+        unsigned int j = 0;
+        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
+        j = __shfl_sync(FULL, j, 0);
+        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
+        if (t64 >= a.n_tiles) break;
+        uint32_t tile = (uint32_t)t64;
+        uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+        const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
+        // this lane's own pixel (validity and the final write); slots carry arbitrary pixels
+        const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
+        const bool my_valid = my_px < a.cam.width && my_py >= a.row_begin && my_py < a.row_end;
+        const unsigned valid_mask = __ballot_sync(FULL, my_valid);
+
+        // reset the pool
+#pragma unroll
+        for (int k = 0; k < P / 32; ++k) pool.state[k * 32 + lane] = SLOT_EMPTY;
+        for (int k = lane; k < 96; k += 32) pool.acc[k] = 0;
+        __syncwarp();
+
+        // work list: item i = sample * nv + k, k-th valid pixel of the tile (nv = 32 for full tiles)
+        const uint32_t nv = (uint32_t)__popc(valid_mask);
+        uint32_t next_item = 0;
+        const uint32_t n_items = (a.max_depth == 0) ? 0u : a.samples * nv;
+
+        // warp-uniform slot census, maintained incrementally
+        int nE = P, nT = 0, nS = 0;
+        // per-lane traversal context (may stay parked across shade / generate phases)
+        bool running = false;
+        int cur = -1, node = B200RT_TRAV_DONE, sp = 0;
+        RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
+        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+        uint32_t nrays = 0, nexh = 0, npaths = 0;
+
+        for (;;) {
+            __syncwarp();
+            const int nRun = __popc(__ballot_sync(FULL, running));
+            const bool can_gen = next_item < n_items && nE > 0;
+            const bool full_gen = next_item < n_items && nE >= 32;
+            if (COUNT) d0 += 1;
+
+            int phase;   // 0 shade, 1 generate, 2 traverse
+            if (nS >= 32) phase = 0;
+            else if (full_gen) phase = 1;
+            else if (nT > 0 || nRun >= T_PARK || (nRun > 0 && nS == 0 && !can_gen)) phase = 2;
+            else if (nS > 0) phase = 0;
+            else if (can_gen) phase = 1;
+            else if (nRun > 0) phase = 2;
+            else break;
+
+            // a ray produced by GENERATE or by SHADE's scatter; stored by the one produce_ray below
+            bool produced = false;
+            int p_slot = -1; uint32_t p_pixel = 0, p_depth = 0;
+            float3 p_o = f3(0, 0, 0), p_d = f3(0, 0, 1), p_atten = f3(1, 1, 1);
+            Rng p_rng; p_rng.state = 0; p_rng.inc = 1;
+
+            if (phase == 1) {
+                // ---- GENERATE: render_scanline's sample loop body, render.rs:60-66 ----
+                int total;
+                int slot = claim_slots<P>(pool, SLOT_EMPTY, true, lane, &total);
+                unsigned gm = __ballot_sync(FULL, slot >= 0);
+                uint32_t take = min((uint32_t)__popc(gm), n_items - next_item);
+                uint32_t my_rank = (uint32_t)__popc(gm & lt);
+                bool have = slot >= 0 && my_rank < take;
+                uint32_t item = next_item + my_rank;
+                next_item += take;
+                if (have) {
+                    uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
+                    uint32_t kth = item - sidx * nv;
+                    uint32_t pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
+                    uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
+                    Rng rng; rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                    float jx = (float)px + rng.gen();
+                    float jy = (float)py + rng.gen();
+                    float3 o, d;
+                    pixel_ray(a.cam, rng, jx, jy, &o, &d);
+                    produced = true; p_slot = slot; p_o = o; p_d = d; p_rng = rng; p_pixel = pl; p_depth = a.max_depth;
+                    ++npaths;
+                }
+                nE -= (int)take; nT += (int)take;
+                if (COUNT) d6 += take;
+            } else if (phase == 2) {
+                // ---- TRAVERSE: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
+                bool do_fetch = true;
+                for (;;) {
+                    // fetch: idle lanes claim waiting slots; the scene-spanning primitives were
+                    // already tested by the producer, so a fetch is 9 loads and 3 reciprocals
+                    if (do_fetch && nT > 0 && __any_sync(FULL, !running)) {
+                        int total;
+                        int slot = claim_slots<P>(pool, SLOT_TRAV, !running, lane, &total);
+                        if (slot >= 0) {
+                            pool.state[slot] = SLOT_RUN;
+                            float3 o = f3(pool.ox[slot], pool.oy[slot], pool.oz[slot]), d = f3(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
+                            ray = FAST ? make_ray_fast(o, d) : make_ray(o, d);
+                            c.t = pool.t[slot]; c.code = pool.code[slot]; c.face = (int)((pool.meta[slot] >> 5) & 7u);
+                            node = 0; sp = 0; cur = slot; running = true;
+                        }
+                        nT -= __popc(__ballot_sync(FULL, slot >= 0));
+                        if (COUNT) d7 += 1;
+                    }
+                    // inner-node steps while enough lanes want one (always at least one step)
+                    bool in = running && node >= 0 && node != B200RT_TRAV_DONE;
+                    if (__any_sync(FULL, in)) {
+                        do {
+                            if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, in)); }
+                            if (in) trav_inner<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                            in = running && node >= 0 && node != B200RT_TRAV_DONE;
+                        } while (__popc(__ballot_sync(FULL, in)) >= T_INNER);
+                    }
+                    // postponed leaves
+                    if (running && node < 0) trav_leaf<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                    // finished traversals: park the slot under its shading kind, release the lane
+                    bool fin = running && node == B200RT_TRAV_DONE;
+                    if (fin) {
+                        uint32_t kind = SK_MISS;
+                        if (c.code >= 0) {
+                            MatRec m = acc.mat((int)((uint32_t)c.code & B200RT_LEAF_ID_MASK));
+                            kind = m.kind == B200RT_MAT_METAL ? SK_METAL : (m.kind == B200RT_MAT_DIELECTRIC ? SK_DIELECTRIC
+                                   : ((m.kind == B200RT_MAT_LAMBERTIAN && m.tex < 0) ? SK_LAMBERT_SOLID : SK_OTHER));
+                        }
+                        pool.t[cur] = c.t; pool.code[cur] = c.code;
+                        pool.meta[cur] = (pool.meta[cur] & ~(7u << 5)) | ((uint32_t)c.face << 5);
+                        pool.state[cur] = SLOT_SHADE0 + kind;
+                        running = false; cur = -1;
+                    }
+                    nS += __popc(__ballot_sync(FULL, fin));
+                    int n_run = __popc(__ballot_sync(FULL, running));
+                    if (nT > 0) do_fetch = (32 - n_run >= F_FETCH) || n_run == 0;   // refill when enough lanes idle
+                    else {
+                        do_fetch = false;
+                        if (n_run == 0) break;
+                        // park the stragglers when a full batch of other work is ready
+                        if (n_run < T_PARK && (nS >= 32 || (next_item < n_items && nE >= 32))) break;
+                    }
+                }
+                continue;
+            } else {
+                // ---- SHADE: ray_color's loop body, render.rs:31-46, one or two kinds per batch ----
+                int cnt[SK_COUNT];
+#pragma unroll
+                for (int q = 0; q < SK_COUNT; ++q) cnt[q] = 0;
+#pragma unroll
+                for (int k = 0; k < P / 32; ++k) {
+                    uint32_t st = pool.state[k * 32 + lane];
+#pragma unroll
+                    for (int q = 0; q < SK_COUNT; ++q) cnt[q] += __popc(__ballot_sync(FULL, st == (uint32_t)(SLOT_SHADE0 + q)));
+                }
+                int k1 = 0;
+#pragma unroll
+                for (int q = 1; q < SK_COUNT; ++q) if (cnt[q] > cnt[k1]) k1 = q;
+                int total;
+                int slot = claim_slots<P>(pool, SLOT_SHADE0 + k1, true, lane, &total);
+                if (COUNT) { d1 += 1; d2 += 1; }
+                if (total < 32) {
+                    int k2 = -1;
+#pragma unroll
+                    for (int q = 0; q < SK_COUNT; ++q) if (q != k1 && cnt[q] > 0 && (k2 < 0 || cnt[q] > cnt[k2])) k2 = q;
+                    if (k2 >= 0) {
+                        int total2;
+                        int slot2 = claim_slots<P>(pool, SLOT_SHADE0 + k2, slot < 0, lane, &total2);
+                        if (slot < 0) slot = slot2;
+                        if (COUNT) d2 += 1;
+                    }
+                }
+                bool have = slot >= 0;
+                int n_have = __popc(__ballot_sync(FULL, have));
+                if (COUNT) d5 += n_have;
+                bool hit = false;
+                HitRec h; h.p = f3(0.f, 0.f, 0.f);
+                ShadePrep sp_; sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
+                RayF r = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
+                float3 atten = f3(1, 1, 1);
+                uint32_t meta = 0;
+                bool cont = false;
+                if (have) {
+                    r = make_ray_shade(f3(pool.ox[slot], pool.oy[slot], pool.oz[slot]), f3(pool.dx[slot], pool.dy[slot], pool.dz[slot]));
+                    atten = f3(pool.ax[slot], pool.ay[slot], pool.az[slot]);
+                    meta = pool.meta[slot];
+                    Closest hc; hc.t = pool.t[slot]; hc.code = pool.code[slot]; hc.face = (int)((meta >> 5) & 7u);
+                    hit = hc.code >= 0;
+                    if (!hit) {
+                        acc_add(pool.acc, meta & 31u, atten * background(a.scene, r.d));
+                    } else {
+                        h = make_hit(r, acc, hc);
+                        sp_ = shade_prepare(a.scene, acc, h);
+                    }
+                }
+                float turb = 0.0f;
+                if (has_perlin) turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+                if (hit) {
+                    Rng rng; rng.state = pool.rs[slot]; rng.inc = pool.ri[slot];
+                    float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
+                    float3 emit = f3(0.f, 0.f, 0.f);
+                    ShadeOut so = shade_finish(r, h, sp_.m, albedo, rng, atten, emit);
+                    if (emit.x != 0.f || emit.y != 0.f || emit.z != 0.f) acc_add(pool.acc, meta & 31u, emit);
+                    uint32_t depth = meta >> 8;
+                    cont = so.scattered;
+                    if (cont) { --depth; if (depth == 0) { cont = false; ++nexh; } }
+                    if (cont) { produced = true; p_slot = slot; p_o = so.o; p_d = so.d; p_atten = atten; p_rng = rng; p_pixel = meta & 31u; p_depth = depth; }
+                }
+                if (have && !cont) pool.state[slot] = SLOT_EMPTY;
+                int n_cont = __popc(__ballot_sync(FULL, cont));
+                nS -= n_have; nT += n_cont; nE += n_have - n_cont;
+            }
+            // the new rays meet the scene-spanning primitives here, in one full uniform batch
+            if (produced) { produce_ray<COUNT, P>(pool, p_slot, acc, top, p_o, p_d, p_atten, p_rng, p_pixel, p_depth, tc); ++nrays; }
+        }
+        __syncwarp();
+        if (my_valid) {
+            const float inv = 1.0f / 4294967296.0f;
+            float4 v = make_float4((float)pool.acc[lane * 3 + 0] * inv, (float)pool.acc[lane * 3 + 1] * inv, (float)pool.acc[lane * 3 + 2] * inv, (float)a.samples);
+            float4* dst = a.accum + (my_py * a.cam.width + my_px);
+            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+        w_rays += nrays; w_exh += nexh; w_paths += npaths;
+    }
+    if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
+    for (int o = 16; o > 0; o >>= 1) {
+        w_rays += __shfl_down_sync(FULL, w_rays, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o);
+        w_exh += __shfl_down_sync(FULL, w_exh, o);
+        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->rays, w_rays);
+        atomicAdd(&a.counters->paths, w_paths);
+        atomicAdd(&a.counters->exhausted, w_exh);
+        if (COUNT) {
+            atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims);
+            atomicAdd(&a.counters->diag[0], d0); atomicAdd(&a.counters->diag[1], d1); atomicAdd(&a.counters->diag[2], d2); atomicAdd(&a.counters->diag[3], d3);
+            atomicAdd(&a.counters->diag[4], d4); atomicAdd(&a.counters->diag[5], d5); atomicAdd(&a.counters->diag[6], d6); atomicAdd(&a.counters->diag[7], d7);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: closest-hit over a ray array, one thread per ray (grid-stride).
 // ------------------------------------------------------------------------------------------
@@ -232,12 +784,13 @@ __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constan
     Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
     int* stack = stack_base + threadIdx.x;
     TravCounters tc; tc.nodes = 0; tc.prims = 0;
+    const TopPrims top = top_of(a.scene);
     unsigned long long nr = 0;
     for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BLOCK) {
         B200rtRay in = a.rays[i];
         RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
         Closest c; c.t = a.t_max; c.code = -1; c.face = 0;
-        closest_hit<COUNT>(ray, acc, stack, BLOCK, a.t_min, c, tc);
+        closest_hit<COUNT>(ray, acc, top, stack, BLOCK, a.t_min, c, tc);
         ++nr;
         int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_LEAF_ID_MASK);
         a.ids[i] = id;
@@ -415,7 +968,8 @@ struct B200rtScene {
     std::mutex mu;
     std::vector<Scratch*> free_scratch;
     std::map<void*, Scratch*> inflight;   // keyed by stream
-    uint32_t max_coord_bits = 0;
+    float box_pad = 0.f;          // how far every BVH box was grown
+    float max_abs_coord = 0.f;    // largest |coordinate| of any primitive box
 };
 
 namespace {
@@ -481,14 +1035,15 @@ int validate(const B200rtSceneDesc* d) {
 }
 
 // shared-memory budget: stage everything when it fits, else the top of the BVH
-SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target) {
+SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target, uint32_t block_threads = BLOCK, size_t extra_bytes = 0) {
     SmemPlan p{};
     const DeviceScene& s = sc->ds;
     size_t budget = sc->smem_optin / blocks_per_sm_target;
     if (budget > sc->smem_optin) budget = sc->smem_optin;
     budget = budget > 2048 ? budget - 1024 : budget;   // per-CTA reserved shared memory
     p.stack_depth = s.bvh_depth + 2;
-    size_t stack_bytes = (size_t)p.stack_depth * BLOCK * sizeof(int);
+    // per-thread stack columns + whatever else the kernel keeps per CTA (v3: the path pools)
+    size_t stack_bytes = (size_t)p.stack_depth * block_threads * sizeof(int) + extra_bytes;
     size_t scene_bytes = (size_t)s.n_nodes * 64 + (size_t)s.n_prims * 64 + (size_t)s.n_tex * 32;
     if (scene_bytes + stack_bytes <= budget) {
         p.all_in_smem = 1; p.n_top = s.n_nodes;
@@ -584,9 +1139,30 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     a.counters = scr->d_counters;
     bool count = (prm->flags & B200RT_FLAG_COUNT_TRAVERSAL) != 0;
 
-    // occupancy: prefer 2 CTAs/SM when the staged scene allows it
-    SmemPlan plan = make_plan(sc, 2);
-    if (!plan.all_in_smem) { SmemPlan p1 = make_plan(sc, 1); if (p1.all_in_smem) plan = p1; }
+    // Tunables (defaults are the measured best; env vars exist for A/B runs under ncu):
+    //   B200RT_KERNEL=1|2   B200RT_BLOCK=256|512|1024   B200RT_TRAV_THRESHOLD=1..32   B200RT_FAST_SLAB=0|1
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    int kernel_version = env_int("B200RT_KERNEL", 2);
+    int block_threads = env_int("B200RT_BLOCK", 768);
+    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 256;
+    if (kernel_version == 1) block_threads = BLOCK;
+    a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 8)));
+    a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 20)));
+    a.wf_fetch = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_FETCH", 8)));
+    a.wf_park = (uint32_t)std::min(33, std::max(0, env_int("B200RT_WF_PARK", 33)));
+    int pool_slots = env_int("B200RT_WF_POOL", 96);
+    if (pool_slots != 64 && pool_slots != 96 && pool_slots != 128) pool_slots = 96;
+    if (kernel_version == 3 && (block_threads != 256 || !getenv("B200RT_BLOCK"))) block_threads = 512;
+    // one-FMA slab planes are conservative only while |origin| * eps stays below the box padding
+    float max_origin = std::max(sc->max_abs_coord, std::max(std::fabs((float)cam->origin[0]), std::max(std::fabs((float)cam->origin[1]), std::fabs((float)cam->origin[2]))));
+    bool fast_ok = sc->box_pad >= 4.0f * 1.1920929e-7f * max_origin;
+    bool fast = fast_ok && env_int("B200RT_FAST_SLAB", 1) != 0;
+
+    uint32_t target_blocks = (block_threads == 256 && kernel_version != 3) ? 2 : 1;
+    size_t extra = kernel_version == 3 ? (size_t)(block_threads / 32) * pool_words(pool_slots) * 4
+                   : (kernel_version == 2 ? (size_t)(block_threads / 32) * 96 * sizeof(long long) : 0);
+    SmemPlan plan = make_plan(sc, target_blocks, block_threads, extra);
+    if (!plan.all_in_smem && target_blocks > 1) { SmemPlan p1 = make_plan(sc, 1, block_threads, extra); if (p1.all_in_smem) plan = p1; }
     a.plan = plan;
 
     scr->launches = 0;
@@ -596,22 +1172,55 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     int blocks_per_sm = 0;
     auto go = [&](auto kernel) -> int {
         int rc = set_smem(kernel, plan.bytes); if (rc) return rc;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, BLOCK, plan.bytes));
-        if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path_trace_kernel does not fit on an SM (smem %u B)", plan.bytes);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, block_threads, plan.bytes));
+        if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path-tracing kernel does not fit on an SM (smem %u B, %d threads)", plan.bytes, block_threads);
+        uint32_t warps_per_block = (uint32_t)block_threads / 32;
         uint32_t warps_needed = (a.n_tiles + a.shard_count - 1) / a.shard_count;
         uint32_t grid = (uint32_t)(sc->sm_count * blocks_per_sm);
-        uint32_t grid_needed = (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32);
+        uint32_t grid_needed = (warps_needed + warps_per_block - 1) / warps_per_block;
         if (grid_needed < grid) grid = grid_needed ? grid_needed : 1;
         CU(cudaEventRecord(scr->ev1, stream));
-        kernel<<<grid, BLOCK, plan.bytes, stream>>>(a);
+        kernel<<<grid, block_threads, plan.bytes, stream>>>(a);
         CU(cudaGetLastError());
         CU(cudaEventRecord(scr->ev2, stream));
         scr->launches += 1;
         return B200RT_OK;
     };
     int rc;
-    if (plan.all_in_smem) rc = count ? go(path_trace_kernel<SmemAcc, true>) : go(path_trace_kernel<SmemAcc, false>);
-    else rc = count ? go(path_trace_kernel<GmemAcc, true>) : go(path_trace_kernel<GmemAcc, false>);
+    if (kernel_version == 3) {
+#define B200RT_GO3(ACC, CNT, FST)                                                                            \
+        (block_threads == 256 ? (pool_slots == 64 ? go(path_trace_kernel_v3<ACC, CNT, FST, 256, 64>)         \
+                                 : pool_slots == 96 ? go(path_trace_kernel_v3<ACC, CNT, FST, 256, 96>)       \
+                                                    : go(path_trace_kernel_v3<ACC, CNT, FST, 256, 128>))     \
+                              : (pool_slots == 64 ? go(path_trace_kernel_v3<ACC, CNT, FST, 512, 64>)         \
+                                 : pool_slots == 96 ? go(path_trace_kernel_v3<ACC, CNT, FST, 512, 96>)       \
+                                                    : go(path_trace_kernel_v3<ACC, CNT, FST, 512, 128>)))
+        if (plan.all_in_smem) {
+            if (count) rc = fast ? B200RT_GO3(SmemAcc, true, true) : B200RT_GO3(SmemAcc, true, false);
+            else rc = fast ? B200RT_GO3(SmemAcc, false, true) : B200RT_GO3(SmemAcc, false, false);
+        } else {
+            if (count) rc = fast ? B200RT_GO3(GmemAcc, true, true) : B200RT_GO3(GmemAcc, true, false);
+            else rc = fast ? B200RT_GO3(GmemAcc, false, true) : B200RT_GO3(GmemAcc, false, false);
+        }
+#undef B200RT_GO3
+    } else if (kernel_version == 1) {
+        if (plan.all_in_smem) rc = count ? go(path_trace_kernel<SmemAcc, true>) : go(path_trace_kernel<SmemAcc, false>);
+        else rc = count ? go(path_trace_kernel<GmemAcc, true>) : go(path_trace_kernel<GmemAcc, false>);
+    } else {
+#define B200RT_GO(ACC, CNT, FST)                                                                             \
+        (block_threads == 256 ? go(path_trace_kernel_v2<ACC, CNT, FST, 256, 2>)                              \
+         : block_threads == 512 ? go(path_trace_kernel_v2<ACC, CNT, FST, 512, 1>)                            \
+         : block_threads == 768 ? go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>)                            \
+                                : go(path_trace_kernel_v2<ACC, CNT, FST, 1024, 1>))
+        if (plan.all_in_smem) {
+            if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
+            else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
+        } else {
+            if (count) rc = fast ? B200RT_GO(GmemAcc, true, true) : B200RT_GO(GmemAcc, true, false);
+            else rc = fast ? B200RT_GO(GmemAcc, false, true) : B200RT_GO(GmemAcc, false, false);
+        }
+#undef B200RT_GO
+    }
     if (rc) return rc;
     CU(cudaMemcpyAsync(scr->h_counters, scr->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     return B200RT_OK;
@@ -624,6 +1233,7 @@ int finish_render(Scratch* scr, cudaStream_t stream, cudaEvent_t end_event, B200
         stats->rays = scr->h_counters->rays; stats->paths = scr->h_counters->paths;
         stats->node_visits = scr->h_counters->nodes; stats->prim_tests = scr->h_counters->prims;
         stats->depth_exhausted = scr->h_counters->exhausted;
+        for (int k = 0; k < 8; ++k) stats->diag[k] = scr->h_counters->diag[k];
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, scr->ev1, scr->ev2)); stats->kernel_ms = ms;
         CU(cudaEventElapsedTime(&ms, scr->ev0, end_event)); stats->total_ms = ms;
@@ -702,9 +1312,27 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         for (int k = 0; k < 3; ++k) { bp.centroid[k] = 0.5f * (b.lo[k] + b.hi[k]); max_abs = std::max(max_abs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))); }
         bprims.push_back(bp);
     }
-    // Grow boxes by ~8 ulp of the scene's largest coordinate so the f32 slab test is
-    // conservative with respect to the f32 primitive tests (a box only culls).
-    float pad = max_abs * 1e-6f;
+    // Scene-spanning primitives leave the BVH for the up-front list (DeviceScene::top_prims):
+    // a box whose surface area is >= 30 % of the whole scene's is met by nearly every ray.
+    DeviceScene ds_top{};
+    {
+        HostBox all; detail::box_init(all);
+        for (auto& bp : bprims) detail::box_grow(all, bp.box);
+        float total = detail::box_area(all);
+        std::vector<BuildPrim> kept;
+        kept.reserve(bprims.size());
+        for (auto& bp : bprims) {
+            if (bprims.size() > 2 && ds_top.n_top_prims < 7 && total > 0.f && detail::box_area(bp.box) >= 0.3f * total)
+                ds_top.top_prims[ds_top.n_top_prims++] = ~bp.code;
+            else kept.push_back(bp);
+        }
+        bprims.swap(kept);
+    }
+    // Grow boxes by 4e-6 x the scene's largest coordinate (~34 ulp): the f32 slab tests are
+    // then conservative with respect to the f32 primitive tests — for the exact form always,
+    // for the one-FMA form (extra error eps * |origin| per axis) while ray origins stay
+    // within ~8x the scene extent (checked per launch).  A box only culls.
+    float pad = max_abs * 4e-6f;
     for (auto& bp : bprims) for (int k = 0; k < 3; ++k) { bp.box.lo[k] -= pad; bp.box.hi[k] += pad; }
     BvhBuildResult bvh = build_bvh(std::move(bprims));
     if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
@@ -749,6 +1377,9 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         memcpy(perlin[i].perm_x, d->perlin[i].perm_x, 256); memcpy(perlin[i].perm_y, d->perlin[i].perm_y, 256); memcpy(perlin[i].perm_z, d->perlin[i].perm_z, 256);
     }
     if ((rc = upload(sc, perlin, &sc->ds.perlin))) return bail(rc);
+    sc->ds.n_top_prims = ds_top.n_top_prims;
+    for (int k = 0; k < 7; ++k) sc->ds.top_prims[k] = ds_top.top_prims[k];
+    sc->box_pad = pad; sc->max_abs_coord = max_abs;
     sc->ds.n_nodes = (uint32_t)nodes.size(); sc->ds.n_prims = d->n_prims; sc->ds.n_tex = d->n_textures; sc->ds.bvh_depth = bvh.depth;
     sc->ds.sky_kind = d->skybox.kind == B200RT_SKY_ABOVE ? B200RT_SKY_ABOVE : B200RT_SKY_FLAT;
     bool flat = d->skybox.kind == B200RT_SKY_FLAT;

@@ -54,6 +54,12 @@ struct DeviceScene {
     const PerlinRec* perlin;
     uint32_t n_nodes, n_prims, n_tex, bvh_depth;
     uint32_t sky_kind; float sky_r, sky_g, sky_b;
+    // Primitives whose box covers most of the scene (the Weekend ground rect and its
+    // dielectric coat box) are not BVH leaves: nearly every ray meets them, so they are
+    // tested up front by all lanes together (no divergence) and their hit bounds the
+    // traversal.  Entries are leaf-encoded (~((type << 28) | id)).  The reference keeps a
+    // linear list beside its tree too (HitList for unbounded objects, scene/mod.rs:61-77).
+    uint32_t n_top_prims; int top_prims[7];
 };
 
 // Camera constants, reduced on the host in f64 from camera/mod.rs:98-114:
@@ -161,16 +167,47 @@ struct Rng {
 // Ray with the per-ray constants hoisted out of Aabb::hit2 (bvh/aabb.rs:66: `1.0 / d` is
 // recomputed per node per axis in the reference) and Sphere::hit (sphere.rs:31: a = d.d).
 // ------------------------------------------------------------------------------------------
+// IEEE-rounded reciprocal, out of line: the primitive tests need it for CPU reproducibility and
+// call it from several places.
+__device__ __noinline__ float rcp_exact(float x) { return __frcp_rn(x); }
+
 struct RayF {
-    float3 o, d, inv;   // inv = 1/d (IEEE, may be +-inf)
-    float a, inv_a;     // d.d and 1/(d.d)
+    float3 o, d;
+    float3 inv;         // 1/d for the BOX tests only: IEEE from make_ray, 1-ulp approximate from
+                        // make_ray_fast (boxes only cull and are padded).  Primitive tests take
+                        // their own IEEE reciprocals so they stay bit-reproducible on the CPU.
+    float3 ood;         // o * inv, for the one-FMA-per-plane slab test
+    float a;            // d.d
 };
 __device__ __forceinline__ RayF make_ray(float3 o, float3 d) {
     RayF r;
     r.o = o; r.d = d;
     r.inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+    r.ood = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
     r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
-    r.inv_a = __frcp_rn(r.a);
+    return r;
+}
+// Traversal-only ray: MUFU.RCP reciprocals (max error 1 ulp) feed aabb_fast, whose boxes are
+// padded by ~34 ulp of the scene extent.  The reciprocal is clamped to +-1e18: with an
+// infinite one (direction component exactly 0) the one-FMA plane distance of an origin inside
+// the slab is inf - inf = NaN on one plane and -inf on the other, which would cull a box the
+// ray is inside of; a huge finite value keeps the far plane at +huge and the error analysis
+// (everything scales with |inv|) unchanged.
+__device__ __forceinline__ float clamp_inv(float x) { return fminf(fmaxf(x, -1e18f), 1e18f); }
+__device__ __forceinline__ RayF make_ray_fast(float3 o, float3 d) {
+    RayF r;
+    r.o = o; r.d = d;
+    r.inv = f3(clamp_inv(__fdividef(1.0f, d.x)), clamp_inv(__fdividef(1.0f, d.y)), clamp_inv(__fdividef(1.0f, d.z)));
+    r.ood = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+    r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
+    return r;
+}
+// Shading-only ray (no reciprocals).
+__device__ __forceinline__ RayF make_ray_shade(float3 o, float3 d) {
+    RayF r;
+    r.o = o; r.d = d;
+    r.inv = f3(0.f, 0.f, 0.f); r.ood = r.inv;
+    r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
     return r;
 }
 
@@ -194,6 +231,22 @@ __device__ __forceinline__ bool aabb_hit2(const RayF& r, float lox, float loy, f
     float hi = fminf(fminf(t1x, t1y), fminf(t1z, t_max));
     *t_enter = lo;
     return !(hi <= lo);
+}
+
+// One-FMA-per-plane slab test used by the render kernels: t = plane * inv - o * inv.
+// Against (plane - o) * inv it carries an extra absolute error of eps * |o * inv| per axis,
+// i.e. eps * |o| in space; the BVH boxes are padded by more than that (scene_create), so a
+// box can only be entered EARLY: the test is conservative and the closest hit unchanged.
+// min/max form (no sign selects); fminf/fmaxf drop NaN planes (0 * inf) like aabb_hit2.
+__device__ __forceinline__ bool aabb_fast(const RayF& r, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                          float t_min, float t_max, float* t_enter) {
+    float ax = fmaf(lox, r.inv.x, -r.ood.x), bx = fmaf(hix, r.inv.x, -r.ood.x);
+    float ay = fmaf(loy, r.inv.y, -r.ood.y), by = fmaf(hiy, r.inv.y, -r.ood.y);
+    float az = fmaf(loz, r.inv.z, -r.ood.z), bz = fmaf(hiz, r.inv.z, -r.ood.z);
+    float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
+    float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_max));
+    *t_enter = lo;
+    return lo <= hi;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,7 +274,8 @@ __device__ __forceinline__ bool accept_t(float t, float t_min, const Closest& c,
 __device__ __forceinline__ bool sphere_roots(const RayF& r, float4 s, float* root_lo, float* root_hi) {
     float ocx = __fsub_rn(r.o.x, s.x), ocy = __fsub_rn(r.o.y, s.y), ocz = __fsub_rn(r.o.z, s.z);
     float bp = -fmaf(ocz, r.d.z, fmaf(ocy, r.d.y, __fmul_rn(ocx, r.d.x)));   // -half_b
-    float q = __fmul_rn(bp, r.inv_a);
+    float inv_a = rcp_exact(r.a);
+    float q = __fmul_rn(bp, inv_a);
     float lx = fmaf(q, r.d.x, ocx), ly = fmaf(q, r.d.y, ocy), lz = fmaf(q, r.d.z, ocz);
     float l2 = fmaf(lz, lz, fmaf(ly, ly, __fmul_rn(lx, lx)));
     float r2 = __fmul_rn(s.w, s.w);
@@ -231,7 +285,7 @@ __device__ __forceinline__ bool sphere_roots(const RayF& r, float4 s, float* roo
     float qq = __fadd_rn(bp, copysignf(sq, bp));
     float c = __fsub_rn(fmaf(ocz, ocz, fmaf(ocy, ocy, __fmul_rn(ocx, ocx))), r2);
     float r0 = __fdiv_rn(c, qq);
-    float r1 = __fmul_rn(qq, r.inv_a);
+    float r1 = __fmul_rn(qq, inv_a);
     *root_lo = fminf(r0, r1);
     *root_hi = fmaxf(r0, r1);
     return true;
@@ -252,7 +306,7 @@ __device__ __forceinline__ void hit_sphere(const RayF& r, float4 s, int id, floa
 __device__ __forceinline__ float rect_t(const RayF& r, int d1, int d2, float d1_min, float d1_max, float d2_min, float d2_max,
                                         float offset, float t_min, float t_max) {
     int dn = 3 - d1 - d2;
-    float t = __fmul_rn(__fsub_rn(offset, comp(r.o, dn)), comp(r.inv, dn));
+    float t = __fmul_rn(__fsub_rn(offset, comp(r.o, dn)), rcp_exact(comp(r.d, dn)));
     if (!(t >= t_min && t <= t_max)) return __int_as_float(0x7fc00000);
     float a = fmaf(t, comp(r.d, d1), comp(r.o, d1));
     float b = fmaf(t, comp(r.d, d2), comp(r.o, d2));
@@ -272,23 +326,30 @@ __device__ __forceinline__ void hit_rect(const RayF& r, uint32_t type, float4 g0
     if (accept_t(t, t_min, c, id)) { c.t = t; c.code = (int)((type << B200RT_LEAF_TYPE_SHIFT) | (uint32_t)id); }
 }
 
-// RectBox::hit (geometry/rect.rs:147-156): the six faces in the reference's order, each
-// against the shrinking interval; a later face replaces an earlier one at equal t.
+// RectBox::hit (geometry/rect.rs:147-156).  The reference takes the closest of its six
+// rects, each against the shrinking interval, a later face replacing an earlier one at equal
+// t (order: z faces, x faces, y faces).  A ray meets a box surface at most at its entry and
+// exit points, so the same answer comes from the three slabs: the entry point if it is
+// inside [t_min, closest], else the exit point; on an edge (equal t) the axis priority
+// y > x > z reproduces "later replaces".  `face` records the normal axis as 0 (z), 2 (x),
+// 4 (y) — the first face index of the reference's pair.
 __device__ __forceinline__ void hit_box(const RayF& r, float4 lo, float4 hi, int id, float t_min, Closest& c) {
-    float best = c.t;
-    int face = -1;
-    // rect.rs:116-127: xy(z = max), xy(z = min), yz(x = max), yz(x = min), xz(y = max), xz(y = min)
-    float t;
-    t = rect_t(r, 0, 1, lo.x, hi.x, lo.y, hi.y, hi.z, t_min, best); if (t <= best) { best = t; face = 0; }
-    t = rect_t(r, 0, 1, lo.x, hi.x, lo.y, hi.y, lo.z, t_min, best); if (t <= best) { best = t; face = 1; }
-    t = rect_t(r, 1, 2, lo.y, hi.y, lo.z, hi.z, hi.x, t_min, best); if (t <= best) { best = t; face = 2; }
-    t = rect_t(r, 1, 2, lo.y, hi.y, lo.z, hi.z, lo.x, t_min, best); if (t <= best) { best = t; face = 3; }
-    t = rect_t(r, 0, 2, lo.x, hi.x, lo.z, hi.z, hi.y, t_min, best); if (t <= best) { best = t; face = 4; }
-    t = rect_t(r, 0, 2, lo.x, hi.x, lo.z, hi.z, lo.y, t_min, best); if (t <= best) { best = t; face = 5; }
-    if (face >= 0 && accept_t(best, t_min, c, id)) {
-        c.t = best; c.face = face;
-        c.code = (int)((B200RT_PRIM_BOX << B200RT_LEAF_TYPE_SHIFT) | (uint32_t)id);
-    }
+    float ix = rcp_exact(r.d.x), iy = rcp_exact(r.d.y), iz = rcp_exact(r.d.z);
+    float ax = __fmul_rn(__fsub_rn(lo.x, r.o.x), ix), bx = __fmul_rn(__fsub_rn(hi.x, r.o.x), ix);
+    float ay = __fmul_rn(__fsub_rn(lo.y, r.o.y), iy), by = __fmul_rn(__fsub_rn(hi.y, r.o.y), iy);
+    float az = __fmul_rn(__fsub_rn(lo.z, r.o.z), iz), bz = __fmul_rn(__fsub_rn(hi.z, r.o.z), iz);
+    float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+    float ny = fminf(ay, by), fy = fmaxf(ay, by);
+    float nz = fminf(az, bz), fz = fmaxf(az, bz);
+    float t_enter = fmaxf(fmaxf(nx, ny), nz), t_exit = fminf(fminf(fx, fy), fz);
+    if (!(t_enter <= t_exit)) return;
+    bool entering = t_enter >= t_min;
+    float t = entering ? t_enter : t_exit;
+    if (!accept_t(t, t_min, c, id)) return;
+    float ty = entering ? ny : fy, tx = entering ? nx : fx;
+    c.t = t;
+    c.face = (ty == t) ? 4 : ((tx == t) ? 2 : 0);
+    c.code = (int)((B200RT_PRIM_BOX << B200RT_LEAF_TYPE_SHIFT) | (uint32_t)id);
 }
 
 // GeometricObject::hit dispatch (geometry/object.rs:44-58)
@@ -319,11 +380,24 @@ __device__ __forceinline__ void hit_leaf(const RayF& r, const Acc& acc, int leaf
 // ------------------------------------------------------------------------------------------
 struct TravCounters { uint32_t nodes, prims; };
 
+struct TopPrims { uint32_t n; int code[7]; };
+
+// The up-front list (DeviceScene::top_prims): same code for every lane, no divergence.
 template <bool COUNT, class Acc>
-__device__ __forceinline__ void closest_hit(const RayF& r, const Acc& acc, int* stack, int stride,
+__device__ __forceinline__ void hit_top_prims(const RayF& r, const Acc& acc, const TopPrims& top, float t_min, Closest& c, TravCounters& tc) {
+#pragma unroll 1
+    for (uint32_t k = 0; k < top.n; ++k) {
+        if (COUNT) tc.prims++;
+        hit_leaf(r, acc, top.code[k], t_min, c);
+    }
+}
+
+template <bool COUNT, class Acc>
+__device__ __forceinline__ void closest_hit(const RayF& r, const Acc& acc, const TopPrims& top, int* stack, int stride,
                                             float t_min, Closest& c, TravCounters& tc) {
     int sp = 0;
     int node = 0;
+    hit_top_prims<COUNT>(r, acc, top, t_min, c, tc);
     for (;;) {
         if (node >= 0) {
             float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
@@ -353,6 +427,51 @@ __device__ __forceinline__ void closest_hit(const RayF& r, const Acc& acc, int* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Resumable traversal for the persistent render kernel.  The cursor (node, sp) lives in
+// registers between calls so a lane can be parked while other lanes of its warp shade.
+// TRAV_DONE marks "no traversal in progress".
+// ------------------------------------------------------------------------------------------
+#define B200RT_TRAV_DONE 0x7fffffff
+
+// One inner-node visit: fetch the node, test both children, descend into the nearer hit
+// child, push the farther one; with no hit, pop (or finish).
+template <bool COUNT, bool FAST, class Acc>
+__device__ __forceinline__ void trav_inner(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, const Closest& c,
+                                           int& node, int& sp, TravCounters& tc) {
+    float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
+    if (COUNT) tc.nodes++;
+    float e0, e1;
+    bool h0, h1;
+    if (FAST) {
+        h0 = aabb_fast(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
+        h1 = aabb_fast(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+    } else {
+        h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
+        h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+    }
+    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+    if (h0 && h1) {
+        bool swap = e1 < e0;
+        stack[sp * stride] = swap ? c0 : c1; ++sp;
+        node = swap ? c1 : c0;
+    } else if (h0 || h1) {
+        node = h0 ? c0 : c1;
+    } else if (sp > 0) {
+        --sp; node = stack[sp * stride];
+    } else {
+        node = B200RT_TRAV_DONE;
+    }
+}
+
+template <bool COUNT, class Acc>
+__device__ __forceinline__ void trav_leaf(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, Closest& c,
+                                          int& node, int& sp, TravCounters& tc) {
+    if (COUNT) tc.prims++;
+    hit_leaf(r, acc, node, t_min, c);
+    if (sp > 0) { --sp; node = stack[sp * stride]; } else node = B200RT_TRAV_DONE;
+}
+
+// ------------------------------------------------------------------------------------------
 // Hit record (geometry/hittable.rs:17-37), built once for the winning primitive.
 // ------------------------------------------------------------------------------------------
 struct HitRec {
@@ -376,7 +495,7 @@ __device__ __forceinline__ HitRec make_hit(const RayF& r, const Acc& acc, const 
     h.p = fma3(c.t, r.d, r.o);                            // Ray::at, vec3.rs:253
     if (h.type == B200RT_PRIM_SPHERE) {
         float4 s = acc.geom0(h.id);
-        float inv_r = __frcp_rn(s.w);                     // sphere.rs:49 `scale(1.0 / radius)`
+        float inv_r = rcp_exact(s.w);                     // sphere.rs:49 `scale(1.0 / radius)`
         // (p - center) / r, evaluated as (oc + t d) / r: one rounding instead of two
         float3 oc = f3(__fsub_rn(r.o.x, s.x), __fsub_rn(r.o.y, s.y), __fsub_rn(r.o.z, s.z));
         float3 hp = fma3(c.t, r.d, oc);
@@ -395,16 +514,22 @@ __device__ __forceinline__ HitRec make_hit(const RayF& r, const Acc& acc, const 
 
 // u,v of the hit (sphere.rs:18-25, rect.rs:71-72) — only image textures read them, so they
 // are computed on demand.
+// Sphere::get_uv (sphere.rs:18-25), out of line: acosf + atan2f are ~200 instructions and only
+// image textures need them.
+__device__ __noinline__ float2 sphere_uv(float nx, float ny_, float nz) {
+    const float PI = 3.14159265358979323846f;
+    float ny = fminf(fmaxf(-ny_, -1.0f), 1.0f);   // f32 rounding can leave |n.y| a hair above 1
+    float theta = acosf(ny);
+    float phi = atan2f(-nz, nx) + PI;
+    return make_float2(phi / (2.0f * PI), theta / PI);
+}
+
 template <class Acc>
 __device__ __forceinline__ void hit_uv(const HitRec& h, const Acc& acc, float* u, float* v) {
-    const float PI = 3.14159265358979323846f;
     if (h.has_uv) { *u = h.uv_u; *v = h.uv_v; return; }
     if (h.type == B200RT_PRIM_SPHERE) {
-        float ny = fminf(fmaxf(-h.n_out.y, -1.0f), 1.0f);   // f32 rounding can leave |n.y| a hair above 1
-        float theta = acosf(ny);
-        float phi = atan2f(-h.n_out.z, h.n_out.x) + PI;
-        *u = phi / (2.0f * PI);
-        *v = theta / PI;
+        float2 uv = sphere_uv(h.n_out.x, h.n_out.y, h.n_out.z);
+        *u = uv.x; *v = uv.y;
     } else {
         float4 g0; int d1, d2;
         if (h.type == B200RT_PRIM_BOX) {
@@ -454,18 +579,67 @@ __device__ __forceinline__ float perlin_turbulence(const PerlinRec* __restrict__
     return fabsf(accum);
 }
 
-// Texture::value.  A checker picks exactly one child per level (checker.rs:27-37), so the
+// One out-of-line copy of the accurate sine (its large-argument path is ~150 instructions and
+// would otherwise be inlined four times): code size is what the instruction cache sees.
+__device__ __noinline__ float sin_accurate(float x) { return sinf(x); }
+
+// Warp-cooperative turbulence.  The marble texture costs 7 octaves x 8 lattice corners = 56
+// gradient terms per evaluation, and in the Weekend scene only the few lanes that hit an odd
+// ground cell need it (ncu: 2.7 of 32 lanes active in the scalar loop).  Here the warp
+// serves the requests one at a time: the 56 terms of one request are spread over the 32
+// lanes (two rounds) and reduced with a butterfly.  Must be called by all 32 lanes.
+__device__ __noinline__ float coop_turbulence(const PerlinRec* __restrict__ tables, bool need, float3 p, int table) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned m = __ballot_sync(FULL, need);
+    float result = 0.0f;
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        float px = __shfl_sync(FULL, p.x, src), py = __shfl_sync(FULL, p.y, src), pz = __shfl_sync(FULL, p.z, src);
+        const PerlinRec* __restrict__ P = tables + __shfl_sync(FULL, table, src);
+        float acc = 0.0f;
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round) {
+            int term = lane + 32 * round;              // (octave << 3) | corner, valid below 56
+            int oct = term >> 3;
+            float sc = (float)(1 << oct);              // tp doubles per octave, perlin/mod.rs:119
+            float wgt = 1.0f / sc;                     // weight halves per octave, :118
+            float x = px * sc, y = py * sc, z = pz * sc;
+            float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+            float u = x - xf, v = y - yf, w = z - zf;
+            int i = __float2int_rz(xf), j = __float2int_rz(yf), k = __float2int_rz(zf);
+            int di = (term >> 2) & 1, dj = (term >> 1) & 1, dk = term & 1;
+            float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+            int idx = P->perm_x[(i + di) & 255] ^ P->perm_y[(j + dj) & 255] ^ P->perm_z[(k + dk) & 255];
+            float4 g = P->ranfloat[idx];
+            float blend = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
+            float term_v = wgt * blend * (g.x * (u - (float)di) + g.y * (v - (float)dj) + g.z * (w - (float)dk));
+            if (term < 56) acc += term_v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == src) result = fabsf(acc);
+    }
+    return result;
+}
+
+// Texture::value, split so the expensive marble can be evaluated cooperatively: the descent
+// resolves solid / checker / image textures on the spot and returns a pending Perlin request
+// otherwise.  A checker picks exactly one child per level (checker.rs:27-37), so the
 // recursion is a loop.
+struct TexResult { float3 rgb; bool need_perlin; int perlin_idx; float perlin_scale; };
+
 template <class Acc>
-__device__ __forceinline__ float3 texture_value(const Acc& acc, const ImageRec* __restrict__ images, const PerlinRec* __restrict__ perlin,
-                                                int t, const HitRec& h) {
+__device__ __forceinline__ TexResult texture_descend(const Acc& acc, const ImageRec* __restrict__ images, int t, const HitRec& h) {
+    TexResult out; out.rgb = f3(0.f, 0.f, 0.f); out.need_perlin = false; out.perlin_idx = 0; out.perlin_scale = 0.f;
     for (;;) {
         TexRec T = acc.texrec(t);
-        if (T.kind == B200RT_TEX_SOLID) return f3(T.r, T.g, T.b);                       // solid.rs:17-21
+        if (T.kind == B200RT_TEX_SOLID) { out.rgb = f3(T.r, T.g, T.b); return out; }   // solid.rs:17-21
         if (T.kind == B200RT_TEX_CHECKER) {                                              // checker.rs:28-36
             // accurate sinf: sizes reach 8/r ~ 160 and coordinates ~ 30
-            float s = sinf(T.scalar * h.p.x) * sinf(T.scalar * h.p.y) * sinf(T.scalar * h.p.z);
-            t = s < 0.0f ? T.odd : T.even;
+            float sn = sin_accurate(T.scalar * h.p.x) * sin_accurate(T.scalar * h.p.y) * sin_accurate(T.scalar * h.p.z);
+            t = sn < 0.0f ? T.odd : T.even;
             continue;
         }
         if (T.kind == B200RT_TEX_IMAGE) {                                                // image_texture.rs:34-56
@@ -479,14 +653,27 @@ __device__ __forceinline__ float3 texture_value(const Acc& acc, const ImageRec* 
             i = min(i, im.width - 1); j = min(j, im.height - 1);
             uchar4 px = __ldg(&im.texels[(size_t)j * im.width + i]);
             const float cs = 1.0f / 255.0f;
-            return f3((float)px.x * cs, (float)px.y * cs, (float)px.z * cs);
+            out.rgb = f3((float)px.x * cs, (float)px.y * cs, (float)px.z * cs);
+            return out;
         }
-        // Perlin marble, perlin/mod.rs:162-184: only the z lane survives the dot with (0,0,1);
-        // the turbulence takes the UNSCALED point (:171).
-        float turb = 10.0f * perlin_turbulence(&perlin[T.image], h.p);
-        float noise = 0.5f * (1.0f + sinf(T.scalar * h.p.z + turb));
-        return f3(noise, noise, noise);
+        out.need_perlin = true; out.perlin_idx = T.image; out.perlin_scale = T.scalar;
+        return out;
     }
+}
+
+// Perlin marble, perlin/mod.rs:162-184: only the z lane survives the dot with (0,0,1); the
+// turbulence takes the UNSCALED point (:171).
+__device__ __forceinline__ float3 marble(float scale, float3 p, float turbulence) {
+    float noise = 0.5f * (1.0f + sin_accurate(scale * p.z + 10.0f * turbulence));
+    return f3(noise, noise, noise);
+}
+
+template <class Acc>
+__device__ __forceinline__ float3 texture_value(const Acc& acc, const ImageRec* __restrict__ images, const PerlinRec* __restrict__ perlin,
+                                                int t, const HitRec& h) {
+    TexResult r = texture_descend(acc, images, t, h);
+    if (r.need_perlin) return marble(r.perlin_scale, h.p, perlin_turbulence(&perlin[r.perlin_idx], h.p));
+    return r.rgb;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,7 +686,7 @@ __device__ __forceinline__ float3 random_in_unit_sphere(Rng& rng) {   // math.rs
     }
 }
 __device__ __forceinline__ float3 unit(float3 v) {   // vec3.rs:170 (nalgebra normalize: divide by the norm)
-    float inv = 1.0f / sqrtf(dot(v, v));
+    float inv = rsqrtf(dot(v, v));                     // MUFU.RSQ, 2 ulp: far inside the 1e-5 scatter tolerance
     return v * inv;
 }
 
@@ -512,17 +699,26 @@ __device__ __forceinline__ float3 background(const DeviceScene& s, float3 d) {
     return f3(s.sky_r, s.sky_g, s.sky_b);   // Flat(c); None is uploaded as Flat(0)
 }
 
-// Material::scatter + ::emitted (material_type.rs:50-79).  Returns false when the path
-// ends (DiffuseLight).  `atten`/`emit` are the ray_color accumulators (render.rs:24-25).
+// Material::scatter + ::emitted (material_type.rs:50-79), in two halves around the (possibly
+// cooperative) texture evaluation.  `atten`/`emit` are ray_color's accumulators
+// (render.rs:24-25).  scattered == false ends the path (DiffuseLight).
 struct ShadeOut { float3 o, d; bool scattered; };
+struct ShadePrep { MatRec m; TexResult tex; };
 
 template <class Acc>
-__device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, const RayF& r, const HitRec& h,
-                                          Rng& rng, float3& atten, float3& emit) {
+__device__ __forceinline__ ShadePrep shade_prepare(const DeviceScene& s, const Acc& acc, const HitRec& h) {
+    ShadePrep p;
+    p.m = acc.mat(h.id);
+    p.tex.rgb = f3(p.m.m0.x, p.m.m0.y, p.m.m0.z);
+    p.tex.need_perlin = false; p.tex.perlin_idx = 0; p.tex.perlin_scale = 0.f;
+    if (p.m.tex >= 0) p.tex = texture_descend(acc, s.images, p.m.tex, h);   // Lambertian / lights with a non-solid texture
+    return p;
+}
+
+__device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h, const MatRec& m, float3 a, Rng& rng, float3& atten, float3& emit) {
     ShadeOut out;
     out.o = h.p;
     out.scattered = true;
-    MatRec m = acc.mat(h.id);
     if (m.kind == B200RT_MAT_DIELECTRIC) {                              // dielectric.rs:22-49
         float ir = m.m0.w;
         float ratio = h.front ? 1.0f / ir : ir;
@@ -548,8 +744,7 @@ __device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, 
         return out;                                                     // attenuation = ones
     }
     if (m.kind == B200RT_MAT_DIFFUSE_LIGHT) {                           // lighting.rs:21-28
-        float3 e = m.tex >= 0 ? texture_value(acc, s.images, s.perlin, m.tex, h) : f3(m.m0.x, m.m0.y, m.m0.z);
-        emit = emit + atten * e;
+        emit = emit + atten * a;
         out.scattered = false;
         out.d = r.d;
         return out;
@@ -563,7 +758,6 @@ __device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, 
         atten = atten * f3(m.m0.x, m.m0.y, m.m0.z);
         return out;
     }
-    float3 a = m.tex >= 0 ? texture_value(acc, s.images, s.perlin, m.tex, h) : f3(m.m0.x, m.m0.y, m.m0.z);
     if (m.kind == B200RT_MAT_FAIRY_LIGHT) {                             // lighting.rs:59-66 then :43-57
         float scale = -dot(h.n, r.d) * rsqrtf(r.a);
         emit = emit + atten * (a * scale);
@@ -574,6 +768,14 @@ __device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, 
     out.d = dir;
     atten = atten * a;
     return out;
+}
+
+template <class Acc>
+__device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, const RayF& r, const HitRec& h,
+                                          Rng& rng, float3& atten, float3& emit) {
+    ShadePrep p = shade_prepare(s, acc, h);
+    float3 a = p.tex.need_perlin ? marble(p.tex.perlin_scale, h.p, perlin_turbulence(&s.perlin[p.tex.perlin_idx], h.p)) : p.tex.rgb;
+    return shade_finish(r, h, p.m, a, rng, atten, emit);
 }
 
 // Camera::pixel_ray (camera/mod.rs:98-131); x, y are the jittered pixel coordinates.
