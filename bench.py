@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="samples per pixel per GPU per step (BASELINE: 500)")
     ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--ref-spp", type=int, default=2, help="spp of the bounded CPU sample per step")
+    ap.add_argument("--ref-spp", type=int, default=16, help="spp of the bounded CPU sample per step")
     ap.add_argument("--cpu-baseline-spp", type=int, default=128, help="bounded CPU sample: ~10-30 s of host work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -269,7 +269,9 @@ def main():
                 torch.cuda.synchronize()
         finally:
             lib.b200rt_scene_destroy(h)
-        return (time.perf_counter() - t0) * 1e3, st.rays
+        ms = (time.perf_counter() - t0) * 1e3
+        log(f"[rank {rank}] e2e step {step}: {ms:.1f} ms wall (kernel {st.kernel_ms:.1f} ms, device total {st.total_ms:.1f} ms)")
+        return ms, st.rays
 
     e2e_step(0)
     if world > 1:

@@ -958,6 +958,14 @@ struct Scratch {                     // per in-flight render: counters, events, 
 
 }  // namespace
 
+// Scratch objects (pinned counters, events, a stream, frame buffers) are pooled per device
+// for the life of the process: creating a scene per frame — what render_scene does — must not
+// pay cudaMallocHost / cudaStreamCreate / a 15 MB cudaMalloc every time.
+namespace {
+std::mutex g_scratch_mu;
+std::map<int, std::vector<Scratch*>> g_scratch_pool;
+}  // namespace
+
 struct B200rtScene {
     int device = 0;
     int sm_count = 0;
@@ -966,7 +974,6 @@ struct B200rtScene {
     B200rtSceneInfo info{};
     std::vector<void*> allocs;
     std::mutex mu;
-    std::vector<Scratch*> free_scratch;
     std::map<void*, Scratch*> inflight;   // keyed by stream
     float box_pad = 0.f;          // how far every BVH box was grown
     float max_abs_coord = 0.f;    // largest |coordinate| of any primitive box
@@ -990,16 +997,14 @@ int resolve_device(int device, int* out) {
     return B200RT_OK;
 }
 
-template <class T> int upload(B200rtScene* sc, const std::vector<T>& host, const T** dev) {
-    void* p = nullptr;
-    size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
-    CU(cudaMalloc(&p, bytes));
-    sc->allocs.push_back(p);
-    sc->info.device_bytes += bytes;
-    if (!host.empty()) CU(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *dev = reinterpret_cast<const T*>(p);
-    return B200RT_OK;
-}
+// Scene arrays are packed into ONE pinned staging buffer and uploaded with ONE copy into ONE
+// device arena (256-byte aligned sub-allocations): a frame that re-creates its scene pays one
+// cudaMalloc + one H2D copy.
+struct Arena {
+    std::vector<uint8_t> host;
+    size_t reserve(size_t bytes) { size_t off = (host.size() + 255) & ~size_t(255); host.resize(off + std::max<size_t>(bytes, 16)); return off; }
+    template <class T> size_t put(const std::vector<T>& v) { size_t off = reserve(v.size() * sizeof(T)); if (!v.empty()) memcpy(host.data() + off, v.data(), v.size() * sizeof(T)); return off; }
+};
 
 int validate(const B200rtSceneDesc* d) {
     if (!d) return fail(B200RT_EINVAL, "scene description is NULL");
@@ -1084,8 +1089,12 @@ int get_scratch(B200rtScene* sc, void* stream_key, Scratch** out) {
     std::lock_guard<std::mutex> lk(sc->mu);
     if (sc->inflight.count(stream_key)) return fail(B200RT_EINVAL, "a render is already in flight on this stream; call b200rt_render_device_finish first");
     Scratch* s = nullptr;
-    if (!sc->free_scratch.empty()) { s = sc->free_scratch.back(); sc->free_scratch.pop_back(); }
-    else {
+    {
+        std::lock_guard<std::mutex> gl(g_scratch_mu);
+        auto& pool = g_scratch_pool[sc->device];
+        if (!pool.empty()) { s = pool.back(); pool.pop_back(); }
+    }
+    if (!s) {
         s = new Scratch();
         cudaError_t e = cudaMalloc(&s->d_counters, sizeof(Counters));
         if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, sizeof(Counters));
@@ -1104,7 +1113,7 @@ void put_scratch(B200rtScene* sc, void* stream_key) {
     std::lock_guard<std::mutex> lk(sc->mu);
     auto it = sc->inflight.find(stream_key);
     if (it == sc->inflight.end()) return;
-    sc->free_scratch.push_back(it->second);
+    { std::lock_guard<std::mutex> gl(g_scratch_mu); g_scratch_pool[sc->device].push_back(it->second); }
     sc->inflight.erase(it);
 }
 
@@ -1347,36 +1356,54 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     B200rtScene* sc = new B200rtScene();
     sc->device = device;
     auto bail = [&](int code) { b200rt_scene_destroy(sc); return code; };
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(B200RT_ECUDA, "cudaGetDeviceProperties failed"));
-    sc->sm_count = prop.multiProcessorCount;
-    sc->smem_optin = prop.sharedMemPerBlockOptin;
+    {   // cudaGetDeviceProperties costs 3-160 ms per call on this driver: two attribute queries instead
+        int sms = 0, optin = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess)
+            return bail(fail(B200RT_ECUDA, "cudaDeviceGetAttribute failed"));
+        sc->sm_count = sms; sc->smem_optin = (size_t)optin;
+    }
 
     static_assert(sizeof(HostNode) == sizeof(BvhNode), "node layout");
     std::vector<BvhNode> nodes(bvh.nodes.size());
     memcpy(nodes.data(), bvh.nodes.data(), nodes.size() * sizeof(BvhNode));
-    if ((rc = upload(sc, nodes, &sc->ds.nodes))) return bail(rc);
-    if ((rc = upload(sc, geom, &sc->ds.geom))) return bail(rc);
-    if ((rc = upload(sc, mats, &sc->ds.mats))) return bail(rc);
-    if ((rc = upload(sc, tex, &sc->ds.tex))) return bail(rc);
+    Arena arena;
+    size_t off_nodes = arena.put(nodes), off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
     // images: RGB8 -> RGBA8 so a texel is one 4-byte load
     std::vector<ImageRec> images(d->n_images);
+    std::vector<size_t> off_img(d->n_images);
     for (uint32_t i = 0; i < d->n_images; ++i) {
         const B200rtImage& im = d->images[i];
         size_t n = (size_t)im.width * im.height;
-        std::vector<uchar4> rgba(n);
+        off_img[i] = arena.reserve(n * sizeof(uchar4));
+        uchar4* rgba = reinterpret_cast<uchar4*>(arena.host.data() + off_img[i]);
         for (size_t k = 0; k < n; ++k) rgba[k] = make_uchar4(im.rgb8[3 * k], im.rgb8[3 * k + 1], im.rgb8[3 * k + 2], 255);
-        const uchar4* dp = nullptr;
-        if ((rc = upload(sc, rgba, &dp))) return bail(rc);
-        images[i].texels = dp; images[i].width = im.width; images[i].height = im.height; images[i].pad = 0;
+        images[i].width = im.width; images[i].height = im.height; images[i].pad = 0;
     }
-    if ((rc = upload(sc, images, &sc->ds.images))) return bail(rc);
     std::vector<PerlinRec> perlin(d->n_perlin);
     for (uint32_t i = 0; i < d->n_perlin; ++i) {
         for (int k = 0; k < 256; ++k) perlin[i].ranfloat[k] = make_float4(d->perlin[i].ranfloat[k][0], d->perlin[i].ranfloat[k][1], d->perlin[i].ranfloat[k][2], 0.f);
         memcpy(perlin[i].perm_x, d->perlin[i].perm_x, 256); memcpy(perlin[i].perm_y, d->perlin[i].perm_y, 256); memcpy(perlin[i].perm_z, d->perlin[i].perm_z, 256);
     }
-    if ((rc = upload(sc, perlin, &sc->ds.perlin))) return bail(rc);
+    size_t off_perlin = arena.put(perlin);
+    size_t off_images = arena.reserve(images.size() * sizeof(ImageRec));
+    uint8_t* dbase = nullptr;
+    {
+        cudaError_t e = cudaMalloc(&dbase, arena.host.size());
+        if (e != cudaSuccess) return bail(fail(B200RT_ENOMEM, "scene arena (%zu B): %s", arena.host.size(), cudaGetErrorString(e)));
+        sc->allocs.push_back(dbase);
+        for (uint32_t i = 0; i < d->n_images; ++i) images[i].texels = reinterpret_cast<const uchar4*>(dbase + off_img[i]);
+        if (!images.empty()) memcpy(arena.host.data() + off_images, images.data(), images.size() * sizeof(ImageRec));
+        e = cudaMemcpy(dbase, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(fail(B200RT_ECUDA, "scene upload: %s", cudaGetErrorString(e)));
+        sc->info.device_bytes = arena.host.size();
+    }
+    sc->ds.nodes = reinterpret_cast<const BvhNode*>(dbase + off_nodes);
+    sc->ds.geom = reinterpret_cast<const GeomRec*>(dbase + off_geom);
+    sc->ds.mats = reinterpret_cast<const MatRec*>(dbase + off_mats);
+    sc->ds.tex = reinterpret_cast<const TexRec*>(dbase + off_tex);
+    sc->ds.images = reinterpret_cast<const ImageRec*>(dbase + off_images);
+    sc->ds.perlin = d->n_perlin ? reinterpret_cast<const PerlinRec*>(dbase + off_perlin) : nullptr;
     sc->ds.n_top_prims = ds_top.n_top_prims;
     for (int k = 0; k < 7; ++k) sc->ds.top_prims[k] = ds_top.top_prims[k];
     sc->box_pad = pad; sc->max_abs_coord = max_abs;
@@ -1395,15 +1422,11 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
 void b200rt_scene_destroy(B200rtScene* sc) {
     if (!sc) return;
     DeviceGuard guard(sc->device);
-    for (auto& kv : sc->inflight) sc->free_scratch.push_back(kv.second);
-    for (Scratch* s : sc->free_scratch) {
-        if (s->own_stream) { cudaStreamSynchronize(s->own_stream); cudaStreamDestroy(s->own_stream); }
-        cudaFree(s->d_counters); cudaFreeHost(s->h_counters);
-        if (s->ev0) cudaEventDestroy(s->ev0); if (s->ev1) cudaEventDestroy(s->ev1); if (s->ev2) cudaEventDestroy(s->ev2); if (s->ev3) cudaEventDestroy(s->ev3);
-        cudaFree(s->d_accum); cudaFree(s->d_rgb);
-        delete s;
+    {   // renders still in flight on this scene: wait, then return their scratch to the pool
+        std::lock_guard<std::mutex> gl(g_scratch_mu);
+        for (auto& kv : sc->inflight) { if (kv.second->own_stream) cudaStreamSynchronize(kv.second->own_stream); g_scratch_pool[sc->device].push_back(kv.second); }
     }
-    for (void* p : sc->allocs) cudaFree(p);
+    if (!sc->allocs.empty()) cudaFree(sc->allocs[0]);   // one arena holds every scene array
     delete sc;
 }
 
@@ -1652,8 +1675,8 @@ int b200rt_fp32_peak(int device, double* lane_instr_per_s) {
     if (!lane_instr_per_s) return fail(B200RT_EINVAL, "NULL argument");
     int rc = resolve_device(device, &device); if (rc) return rc;
     DeviceGuard guard(device);
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
-    int grid = prop.multiProcessorCount * 8, iters = 4096;
+    int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    int grid = sms * 8, iters = 4096;
     DevBuf o; if ((rc = o.alloc((size_t)grid * 256 * 4))) return rc;
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     double best = 0.0;
