@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
             for (;;) {
                 if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
+                // (a warp-uniform inner loop that stops below a lane threshold was measured too:
+                //  18 lanes per step instead of 13, but 8 % slower overall — profiles/README.md)
                 while (node >= 0 && node != B200RT_TRAV_DONE) {
                     if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
                     trav_inner<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
@@ -368,7 +370,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 sp_ = shade_prepare(a.scene, acc, h);
             }
             float turb = 0.0f;
-            if (has_perlin) turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+            if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))   // warp-uniform: skip the call when no lane asks
+                turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
             if (hit) {
                 float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
                 ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
@@ -720,7 +723,8 @@ __global__ void __launch_bounds__(BLK, 1) path_trace_kernel_v3(const __grid_cons
                     }
                 }
                 float turb = 0.0f;
-                if (has_perlin) turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+                if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))
+                    turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
                 if (hit) {
                     Rng rng; rng.state = pool.rs[slot]; rng.inc = pool.ri[slot];
                     float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
@@ -1153,10 +1157,10 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     int kernel_version = env_int("B200RT_KERNEL", 2);
     int block_threads = env_int("B200RT_BLOCK", 768);
-    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 256;
+    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
     if (kernel_version == 1) block_threads = BLOCK;
-    a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 8)));
-    a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 20)));
+    a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 4)));
+    a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
     a.wf_fetch = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_FETCH", 8)));
     a.wf_park = (uint32_t)std::min(33, std::max(0, env_int("B200RT_WF_PARK", 33)));
     int pool_slots = env_int("B200RT_WF_POOL", 96);

@@ -169,7 +169,7 @@ struct Rng {
 // ------------------------------------------------------------------------------------------
 // IEEE-rounded reciprocal, out of line: the primitive tests need it for CPU reproducibility and
 // call it from several places.
-__device__ __noinline__ float rcp_exact(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
 
 struct RayF {
     float3 o, d;
