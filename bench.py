@@ -303,8 +303,11 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         roofline = {"bound": "fp32-issue", "achieved": achieved / 1e12, "peak": fp32_peak / 1e12, "unit": "Tlane-op/s",
-                    "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
-                    "kernel": "path_trace_kernel", "kernel_ms": float(np.mean(kernel_ms)),
+                    "frac": achieved / fp32_peak if fp32_peak else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
+                    # profiles/r01_ncu_metrics.md): the scene is staged in shared memory, HBM is idle
+                    "traffic": 543744, "traffic_unit": "bytes per launch (ncu capture of a 50-spp launch)",
+                    "kernel": "path_trace_kernel_v2", "kernel_ms": float(np.mean(kernel_ms)),
                     "ops_per_ray": ops_per_ray, "node_visits_per_ray": cst.node_visits / cst.rays, "prim_tests_per_ray": cst.prim_tests / cst.rays,
                     "segments_per_sample": cst.rays / cst.paths,
                     "peak_source": "FFMA-chain microbenchmark run live in this process (b200rt_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
