@@ -16,10 +16,15 @@ ORACLE    := oracle/liboracle.so
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 HOST_HDRS := $(wildcard $(HOST)/*.hpp) include/b200rt.h include/b200rt_host.h
 
-all: lib oracle
+all: lib oracle cli
 
 lib: $(LIB)
 oracle: $(ORACLE)
+cli: ray-cli
+
+# `ray-cli`-compatible front end (src/main.rs, src/argparse.rs, src/scenes.rs of the reference)
+ray-cli: $(PKG)/cli/ray_cli.cpp $(LIB) $(HOST_HDRS)
+	$(HOSTCXX) $(CXXFLAGS) -o $@ $< -L$(PKG) -lb200rt -Wl,-rpath,'$$ORIGIN/$(PKG)'
 
 build/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/rt_device.cuh $(CSRC)/bvh_build.hpp include/b200rt.h
 	@mkdir -p build
@@ -46,4 +51,4 @@ $(ORACLE): oracle/oracle_capi.cpp oracle/oracle.hpp oracle/gpu_f32.hpp oracle/or
 clean:
 	rm -rf build $(LIB) $(ORACLE) ray-cli
 
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle cli clean
