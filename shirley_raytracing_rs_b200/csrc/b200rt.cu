@@ -1157,7 +1157,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     int kernel_version = env_int("B200RT_KERNEL", 2);
     int block_threads = env_int("B200RT_BLOCK", 768);
-    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
+    if (block_threads % 32 != 0 || block_threads < 256 || block_threads > 1024) block_threads = 768;
     if (kernel_version == 1) block_threads = BLOCK;
     a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 4)));
     a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
@@ -1223,8 +1223,13 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
 #define B200RT_GO(ACC, CNT, FST)                                                                             \
         (block_threads == 256 ? go(path_trace_kernel_v2<ACC, CNT, FST, 256, 2>)                              \
          : block_threads == 512 ? go(path_trace_kernel_v2<ACC, CNT, FST, 512, 1>)                            \
-         : block_threads == 768 ? go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>)                            \
-                                : go(path_trace_kernel_v2<ACC, CNT, FST, 1024, 1>))
+         : block_threads == 672 ? go(path_trace_kernel_v2<ACC, CNT, FST, 672, 1>)                            \
+         : block_threads == 704 ? go(path_trace_kernel_v2<ACC, CNT, FST, 704, 1>)                            \
+         : block_threads == 736 ? go(path_trace_kernel_v2<ACC, CNT, FST, 736, 1>)                            \
+         : block_threads == 800 ? go(path_trace_kernel_v2<ACC, CNT, FST, 800, 1>)                            \
+         : block_threads == 832 ? go(path_trace_kernel_v2<ACC, CNT, FST, 832, 1>)                            \
+         : block_threads == 1024 ? go(path_trace_kernel_v2<ACC, CNT, FST, 1024, 1>)                          \
+                                : go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>))
         if (plan.all_in_smem) {
             if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
             else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
