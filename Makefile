@@ -6,6 +6,10 @@ NVCC      ?= nvcc
 HOSTCXX   ?= /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+# make DEV=1: compile only the default render-kernel variant (fast iteration)
+ifdef DEV
+NVFLAGS   += -DB200RT_DEV_BUILD
+endif
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Wno-unused-function
 PKG       := shirley_raytracing_rs_b200
 CSRC      := $(PKG)/csrc

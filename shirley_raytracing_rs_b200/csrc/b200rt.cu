@@ -301,62 +301,22 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         TravCounters tc; tc.nodes = 0; tc.prims = 0;
         bool alive = false;
         Rng rng; rng.state = 0; rng.inc = 1;
-        RayF ray = make_ray(f3(0, 0, 0), f3(0, 0, 1));
+        RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
         uint32_t depth = 0;
-        int node = B200RT_TRAV_DONE, sp = 0;
+        int node = B200RT_TRAV_DONE, sp = 1;
         Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+        stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
 
+        // One outer iteration = shade the lanes whose traversal finished, hand new paths to the
+        // lanes without one, set up the new segments of BOTH groups together (one copy of the ray
+        // set-up + up-front primitive code, run at ~30 lanes instead of twice at 6 and 18), traverse.
         for (;;) {
-            // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
-            unsigned want_m = __ballot_sync(FULL, !alive);
-            uint32_t item = next_item + (uint32_t)__popc(want_m & lt);
-            bool regen = !alive && item < n_items;
-            next_item = min(n_items, next_item + (uint32_t)__popc(want_m));
-            if (COUNT) { d0 += 1; d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
-            if (regen) {
-                uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
-                uint32_t kth = item - sidx * nv;
-                pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
-                uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
-                rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
-                float jx = (float)px + rng.gen();
-                float jy = (float)py + rng.gen();
-                float3 o, d;
-                pixel_ray(a.cam, rng, jx, jy, &o, &d);
-                ray = FAST ? make_ray_fast(o, d) : make_ray(o, d);
-                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
-                depth = a.max_depth;
-                alive = depth > 0;
-                ++npaths;
-                if (alive) {                          // first segment
-                    c.t = INFINITY; c.code = -1; c.face = 0;
-                    hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc);
-                    node = 0; sp = 0; ++nrays;
-                }
-            }
-            if (!__any_sync(FULL, alive)) break;
-            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
-
-            // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
-            for (;;) {
-                if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
-                // (a warp-uniform inner loop that stops below a lane threshold was measured too:
-                //  18 lanes per step instead of 13, but 8 % slower overall — profiles/README.md)
-                while (node >= 0 && node != B200RT_TRAV_DONE) {
-                    if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
-                    trav_inner<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
-                }
-                if (node < 0) trav_leaf<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
-                unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
-                if ((uint32_t)__popc(still) < a.trav_threshold) break;
-            }
-
-            // ---- shade the lanes whose traversal finished: ray_color's loop body, render.rs:31-46 ----
+            // ---- shade: ray_color's loop body, render.rs:31-46 ----
             bool fin = alive && node == B200RT_TRAV_DONE;
-            if (COUNT) d5 += __popc(__ballot_sync(FULL, fin));
+            if (COUNT) { d0 += 1; d5 += __popc(__ballot_sync(FULL, fin)); }
             bool hit = fin && c.code >= 0;
-            bool done = false;
+            bool done = false, setup = false;
             HitRec h;
             ShadePrep sp_;
             sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
@@ -378,15 +338,61 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 done = !so.scattered;
                 if (!done) {
                     if (--depth == 0) { done = true; ++nexh; }
-                    else {
-                        ray = FAST ? make_ray_fast(so.o, so.d) : make_ray(so.o, so.d);
-                        c.t = INFINITY; c.code = -1; c.face = 0;
-                        hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc);
-                        node = 0; sp = 0; ++nrays;
-                    }
+                    else { ray.o = so.o; ray.d = so.d; setup = true; }
                 }
             }
-            if (done) { acc_add(wacc, pl, emit); alive = false; node = B200RT_TRAV_DONE; }
+            if (done) { acc_add(wacc, pl, emit); alive = false; }
+
+            // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
+            unsigned want_m = __ballot_sync(FULL, !alive);
+            uint32_t item = next_item + (uint32_t)__popc(want_m & lt);
+            bool regen = !alive && item < n_items;
+            next_item = min(n_items, next_item + (uint32_t)__popc(want_m));
+            if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
+            if (regen) {
+                uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
+                uint32_t kth = item - sidx * nv;
+                pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
+                uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
+                rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                float jx = (float)px + rng.gen();
+                float jy = (float)py + rng.gen();
+                pixel_ray(a.cam, rng, jx, jy, &ray.o, &ray.d);
+                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
+                depth = a.max_depth;
+                alive = depth > 0;
+                setup = alive;
+                ++npaths;
+            }
+            if (!__any_sync(FULL, alive)) break;
+            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
+
+            // ---- new segment: per-ray constants, then the scene-spanning primitives ----
+            if (setup) {
+                // IEEE reciprocals, taken once: the up-front rect/box tests need exactly these
+                // (bit-reproducible on the CPU), and the slab tests take them too
+                float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
+                ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
+                ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
+                ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
+                c.t = INFINITY; c.code = -1; c.face = 0;
+                hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc, &inv_e);
+                node = 0; sp = 1; ++nrays;
+            }
+
+            // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
+            for (;;) {
+                if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
+                // (a warp-uniform inner loop that stops below a lane threshold was measured too:
+                //  18 lanes per step instead of 13, but 8 % slower overall — profiles/README.md)
+                while (node >= 0 && node != B200RT_TRAV_DONE) {
+                    if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
+                    trav_inner_s<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                }
+                if (node < 0) trav_leaf_s<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
+                if ((uint32_t)__popc(still) < a.trav_threshold) break;
+            }
         }
         __syncwarp();
         if (valid) {
@@ -1050,7 +1056,7 @@ SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target, uint32_
     size_t budget = sc->smem_optin / blocks_per_sm_target;
     if (budget > sc->smem_optin) budget = sc->smem_optin;
     budget = budget > 2048 ? budget - 1024 : budget;   // per-CTA reserved shared memory
-    p.stack_depth = s.bvh_depth + 2;
+    p.stack_depth = s.bvh_depth + 3;   // + the sentinel entry of the v2 kernel
     // per-thread stack columns + whatever else the kernel keeps per CTA (v3: the path pools)
     size_t stack_bytes = (size_t)p.stack_depth * block_threads * sizeof(int) + extra_bytes;
     size_t scene_bytes = (size_t)s.n_nodes * 64 + (size_t)s.n_prims * 64 + (size_t)s.n_tex * 32;
@@ -1157,7 +1163,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     int kernel_version = env_int("B200RT_KERNEL", 2);
     int block_threads = env_int("B200RT_BLOCK", 768);
-    if (block_threads % 32 != 0 || block_threads < 256 || block_threads > 1024) block_threads = 768;
+    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
     if (kernel_version == 1) block_threads = BLOCK;
     a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 4)));
     a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
@@ -1200,6 +1206,20 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         return B200RT_OK;
     };
     int rc;
+#ifdef B200RT_DEV_BUILD
+    // `make DEV=1`: only the default variant, for fast edit-compile-measure loops
+    if (kernel_version != 2) return fail(B200RT_EINVAL, "dev build: only B200RT_KERNEL=2 is compiled");
+    block_threads = 768;
+#define B200RT_GO(ACC, CNT, FST) go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>)
+    if (plan.all_in_smem) {
+        if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
+        else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
+    } else {
+        if (count) rc = fast ? B200RT_GO(GmemAcc, true, true) : B200RT_GO(GmemAcc, true, false);
+        else rc = fast ? B200RT_GO(GmemAcc, false, true) : B200RT_GO(GmemAcc, false, false);
+    }
+#undef B200RT_GO
+#else
     if (kernel_version == 3) {
 #define B200RT_GO3(ACC, CNT, FST)                                                                            \
         (block_threads == 256 ? (pool_slots == 64 ? go(path_trace_kernel_v3<ACC, CNT, FST, 256, 64>)         \
@@ -1223,11 +1243,6 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
 #define B200RT_GO(ACC, CNT, FST)                                                                             \
         (block_threads == 256 ? go(path_trace_kernel_v2<ACC, CNT, FST, 256, 2>)                              \
          : block_threads == 512 ? go(path_trace_kernel_v2<ACC, CNT, FST, 512, 1>)                            \
-         : block_threads == 672 ? go(path_trace_kernel_v2<ACC, CNT, FST, 672, 1>)                            \
-         : block_threads == 704 ? go(path_trace_kernel_v2<ACC, CNT, FST, 704, 1>)                            \
-         : block_threads == 736 ? go(path_trace_kernel_v2<ACC, CNT, FST, 736, 1>)                            \
-         : block_threads == 800 ? go(path_trace_kernel_v2<ACC, CNT, FST, 800, 1>)                            \
-         : block_threads == 832 ? go(path_trace_kernel_v2<ACC, CNT, FST, 832, 1>)                            \
          : block_threads == 1024 ? go(path_trace_kernel_v2<ACC, CNT, FST, 1024, 1>)                          \
                                 : go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>))
         if (plan.all_in_smem) {
@@ -1239,6 +1254,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         }
 #undef B200RT_GO
     }
+#endif
     if (rc) return rc;
     CU(cudaMemcpyAsync(scr->h_counters, scr->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     return B200RT_OK;

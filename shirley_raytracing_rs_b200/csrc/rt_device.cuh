@@ -303,10 +303,12 @@ __device__ __forceinline__ void hit_sphere(const RayF& r, float4 s, int id, floa
 
 // Rect<D1,D2>::hit (geometry/rect.rs:55-80) for the plane `offset` on axis dn with in-plane
 // axes d1, d2.  Returns t or NaN.
+// `inv_e`, when given, holds the IEEE reciprocals 1/d already taken for this ray (the render
+// kernel shares them between the up-front primitives); the value is the same __frcp_rn either way.
 __device__ __forceinline__ float rect_t(const RayF& r, int d1, int d2, float d1_min, float d1_max, float d2_min, float d2_max,
-                                        float offset, float t_min, float t_max) {
+                                        float offset, float t_min, float t_max, const float3* inv_e = nullptr) {
     int dn = 3 - d1 - d2;
-    float t = __fmul_rn(__fsub_rn(offset, comp(r.o, dn)), rcp_exact(comp(r.d, dn)));
+    float t = __fmul_rn(__fsub_rn(offset, comp(r.o, dn)), inv_e ? comp(*inv_e, dn) : rcp_exact(comp(r.d, dn)));
     if (!(t >= t_min && t <= t_max)) return __int_as_float(0x7fc00000);
     float a = fmaf(t, comp(r.d, d1), comp(r.o, d1));
     float b = fmaf(t, comp(r.d, d2), comp(r.o, d2));
@@ -319,10 +321,11 @@ __device__ __forceinline__ void rect_axes(uint32_t type, int& d1, int& d2) {
     d2 = (type == B200RT_PRIM_RECT_XY) ? 1 : 2;
 }
 
-__device__ __forceinline__ void hit_rect(const RayF& r, uint32_t type, float4 g0, float offset, int id, float t_min, Closest& c) {
+__device__ __forceinline__ void hit_rect(const RayF& r, uint32_t type, float4 g0, float offset, int id, float t_min, Closest& c,
+                                         const float3* inv_e = nullptr) {
     int d1, d2;
     rect_axes(type, d1, d2);
-    float t = rect_t(r, d1, d2, g0.x, g0.y, g0.z, g0.w, offset, t_min, c.t);
+    float t = rect_t(r, d1, d2, g0.x, g0.y, g0.z, g0.w, offset, t_min, c.t, inv_e);
     if (accept_t(t, t_min, c, id)) { c.t = t; c.code = (int)((type << B200RT_LEAF_TYPE_SHIFT) | (uint32_t)id); }
 }
 
@@ -333,8 +336,8 @@ __device__ __forceinline__ void hit_rect(const RayF& r, uint32_t type, float4 g0
 // inside [t_min, closest], else the exit point; on an edge (equal t) the axis priority
 // y > x > z reproduces "later replaces".  `face` records the normal axis as 0 (z), 2 (x),
 // 4 (y) — the first face index of the reference's pair.
-__device__ __forceinline__ void hit_box(const RayF& r, float4 lo, float4 hi, int id, float t_min, Closest& c) {
-    float ix = rcp_exact(r.d.x), iy = rcp_exact(r.d.y), iz = rcp_exact(r.d.z);
+__device__ __forceinline__ void hit_box(const RayF& r, float4 lo, float4 hi, int id, float t_min, Closest& c, const float3* inv_e = nullptr) {
+    float ix = inv_e ? inv_e->x : rcp_exact(r.d.x), iy = inv_e ? inv_e->y : rcp_exact(r.d.y), iz = inv_e ? inv_e->z : rcp_exact(r.d.z);
     float ax = __fmul_rn(__fsub_rn(lo.x, r.o.x), ix), bx = __fmul_rn(__fsub_rn(hi.x, r.o.x), ix);
     float ay = __fmul_rn(__fsub_rn(lo.y, r.o.y), iy), by = __fmul_rn(__fsub_rn(hi.y, r.o.y), iy);
     float az = __fmul_rn(__fsub_rn(lo.z, r.o.z), iz), bz = __fmul_rn(__fsub_rn(hi.z, r.o.z), iz);
@@ -354,7 +357,7 @@ __device__ __forceinline__ void hit_box(const RayF& r, float4 lo, float4 hi, int
 
 // GeometricObject::hit dispatch (geometry/object.rs:44-58)
 template <class Acc>
-__device__ __forceinline__ void hit_leaf(const RayF& r, const Acc& acc, int leaf, float t_min, Closest& c) {
+__device__ __forceinline__ void hit_leaf(const RayF& r, const Acc& acc, int leaf, float t_min, Closest& c, const float3* inv_e = nullptr) {
     uint32_t code = (uint32_t)~leaf;
     uint32_t type = code >> B200RT_LEAF_TYPE_SHIFT;
     int id = (int)(code & B200RT_LEAF_ID_MASK);
@@ -364,8 +367,8 @@ __device__ __forceinline__ void hit_leaf(const RayF& r, const Acc& acc, int leaf
         hit_sphere(r, g0, id, t_min, c);
     } else {
         float4 g1 = acc.geom1(id);
-        if (type == B200RT_PRIM_BOX) hit_box(r, g0, g1, id, t_min, c);
-        else hit_rect(r, type, g0, g1.x, id, t_min, c);
+        if (type == B200RT_PRIM_BOX) hit_box(r, g0, g1, id, t_min, c, inv_e);
+        else hit_rect(r, type, g0, g1.x, id, t_min, c, inv_e);
     }
 }
 
@@ -384,11 +387,12 @@ struct TopPrims { uint32_t n; int code[7]; };
 
 // The up-front list (DeviceScene::top_prims): same code for every lane, no divergence.
 template <bool COUNT, class Acc>
-__device__ __forceinline__ void hit_top_prims(const RayF& r, const Acc& acc, const TopPrims& top, float t_min, Closest& c, TravCounters& tc) {
+__device__ __forceinline__ void hit_top_prims(const RayF& r, const Acc& acc, const TopPrims& top, float t_min, Closest& c, TravCounters& tc,
+                                              const float3* inv_e = nullptr) {
 #pragma unroll 1
     for (uint32_t k = 0; k < top.n; ++k) {
         if (COUNT) tc.prims++;
-        hit_leaf(r, acc, top.code[k], t_min, c);
+        hit_leaf(r, acc, top.code[k], t_min, c, inv_e);
     }
 }
 
@@ -461,6 +465,42 @@ __device__ __forceinline__ void trav_inner(const RayF& r, const Acc& acc, int* s
     } else {
         node = B200RT_TRAV_DONE;
     }
+}
+
+// Variants for a stack whose element 0 holds B200RT_TRAV_DONE (sp starts at 1): a pop needs no
+// emptiness test, the sentinel ends the traversal.
+template <bool COUNT, bool FAST, class Acc>
+__device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, const Closest& c,
+                                             int& node, int& sp, TravCounters& tc) {
+    float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
+    if (COUNT) tc.nodes++;
+    float e0, e1;
+    bool h0, h1;
+    if (FAST) {
+        h0 = aabb_fast(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
+        h1 = aabb_fast(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+    } else {
+        h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
+        h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+    }
+    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+    if (h0 && h1) {
+        bool swap = e1 < e0;
+        stack[sp * stride] = swap ? c0 : c1; ++sp;
+        node = swap ? c1 : c0;
+    } else if (h0 || h1) {
+        node = h0 ? c0 : c1;
+    } else {
+        --sp; node = stack[sp * stride];
+    }
+}
+
+template <bool COUNT, class Acc>
+__device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, Closest& c,
+                                            int& node, int& sp, TravCounters& tc) {
+    if (COUNT) tc.prims++;
+    hit_leaf(r, acc, node, t_min, c);
+    --sp; node = stack[sp * stride];
 }
 
 template <bool COUNT, class Acc>
@@ -583,43 +623,59 @@ __device__ __forceinline__ float perlin_turbulence(const PerlinRec* __restrict__
 // would otherwise be inlined four times): code size is what the instruction cache sees.
 __device__ __noinline__ float sin_accurate(float x) { return sinf(x); }
 
-// Warp-cooperative turbulence.  The marble texture costs 7 octaves x 8 lattice corners = 56
-// gradient terms per evaluation, and in the Weekend scene only the few lanes that hit an odd
-// ground cell need it (ncu: 2.7 of 32 lanes active in the scalar loop).  Here the warp
-// serves the requests one at a time: the 56 terms of one request are spread over the 32
-// lanes (two rounds) and reduced with a butterfly.  Must be called by all 32 lanes.
+// CheckerTexture::value (checker.rs:27-37) only looks at the SIGN of sin(s x) sin(s y) sin(s z):
+// negative iff an odd number of the sines is negative, and sin(a) < 0 iff floor(a / pi) is odd.
+// Three multiplies and floors instead of three accurate sines (arguments reach ~5e3: size 8/r
+// up to 160, coordinates up to 30 — SURVEY.md §8a a17).  sin(a) is exactly 0 only at a == 0,
+// where the product is +-0 and the reference takes `even`.  The cell a point falls in can
+// differ from the f64 reference only within |a| * 2^-23 of a zero crossing, the same order as
+// the rounding of the hit point itself.
+__device__ __forceinline__ bool checker_odd(float size, float3 p) {
+    const float INV_PI = 0.318309886183790671538f;
+    float ax = size * p.x, ay = size * p.y, az = size * p.z;
+    int k = __float2int_rd(ax * INV_PI) ^ __float2int_rd(ay * INV_PI) ^ __float2int_rd(az * INV_PI);
+    bool zero = ax == 0.0f || ay == 0.0f || az == 0.0f;
+    return (k & 1) && !zero;
+}
+
+// Warp-cooperative turbulence.  The marble texture costs 7 octaves x 8 lattice corners per
+// evaluation, and in the Weekend scene only the few lanes that hit an odd ground cell need it
+// (ncu on the per-lane loop: 2.7 of 32 lanes active).  Here the warp serves up to four requests
+// per round: lane = 7 * slot + octave evaluates one full octave (perlin/mod.rs:87-109 at
+// p * 2^octave, weight 2^-octave — :118-119) of the slot's request, the seven octave terms are
+// summed inside each group of seven lanes and handed back to the requesting lane.  (The first
+// cut spread the 56 (octave, corner) terms of ONE request over the warp: two 75-instruction
+// rounds per request, 9 % of the kernel's issue slots.)  Must be called by all 32 lanes.
 __device__ __noinline__ float coop_turbulence(const PerlinRec* __restrict__ tables, bool need, float3 p, int table) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const int slot = (lane * 37) >> 8;                 // lane / 7 for lane < 32
+    const int oct = lane - slot * 7;
+    const float sc = (float)(1 << oct), wgt = 1.0f / sc;
     unsigned m = __ballot_sync(FULL, need);
     float result = 0.0f;
     while (m) {
-        int src = __ffs(m) - 1;
-        m &= m - 1;
+        // the four lowest requesting lanes (a missing one repeats the first: its group's work is discarded)
+        int s0 = __ffs(m) - 1;
+        unsigned m1 = m & (m - 1);
+        int s1 = m1 ? __ffs(m1) - 1 : s0;
+        unsigned m2 = m1 & (m1 - 1);
+        int s2 = m2 ? __ffs(m2) - 1 : s0;
+        unsigned m3 = m2 & (m2 - 1);
+        int s3 = m3 ? __ffs(m3) - 1 : s0;
+        unsigned rest = m3 & (m3 - 1);
+        unsigned served = m ^ rest;
+        m = rest;
+        int src = slot == 0 ? s0 : (slot == 1 ? s1 : (slot == 2 ? s2 : s3));
         float px = __shfl_sync(FULL, p.x, src), py = __shfl_sync(FULL, p.y, src), pz = __shfl_sync(FULL, p.z, src);
         const PerlinRec* __restrict__ P = tables + __shfl_sync(FULL, table, src);
-        float acc = 0.0f;
-#pragma unroll 1
-        for (int round = 0; round < 2; ++round) {
-            int term = lane + 32 * round;              // (octave << 3) | corner, valid below 56
-            int oct = term >> 3;
-            float sc = (float)(1 << oct);              // tp doubles per octave, perlin/mod.rs:119
-            float wgt = 1.0f / sc;                     // weight halves per octave, :118
-            float x = px * sc, y = py * sc, z = pz * sc;
-            float xf = floorf(x), yf = floorf(y), zf = floorf(z);
-            float u = x - xf, v = y - yf, w = z - zf;
-            int i = __float2int_rz(xf), j = __float2int_rz(yf), k = __float2int_rz(zf);
-            int di = (term >> 2) & 1, dj = (term >> 1) & 1, dk = term & 1;
-            float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
-            int idx = P->perm_x[(i + di) & 255] ^ P->perm_y[(j + dj) & 255] ^ P->perm_z[(k + dk) & 255];
-            float4 g = P->ranfloat[idx];
-            float blend = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
-            float term_v = wgt * blend * (g.x * (u - (float)di) + g.y * (v - (float)dj) + g.z * (w - (float)dk));
-            if (term < 56) acc += term_v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-        if (lane == src) result = fabsf(acc);
+        float v = wgt * perlin_noise(P, f3(px * sc, py * sc, pz * sc));
+        float t4 = __shfl_down_sync(FULL, v, 4); if (oct < 3) v += t4;     // (0,4) (1,5) (2,6) (3)
+        float t2 = __shfl_down_sync(FULL, v, 2); if (oct < 2) v += t2;     // (0,4,2,6) (1,5,3)
+        float t1 = __shfl_down_sync(FULL, v, 1); if (oct < 1) v += t1;     // all seven at the group's first lane
+        int rank = __popc(served & ((1u << lane) - 1u));                  // which slot served this lane's request
+        float got = __shfl_sync(FULL, v, rank * 7);
+        if ((served >> lane) & 1u) result = fabsf(got);
     }
     return result;
 }
@@ -637,9 +693,7 @@ __device__ __forceinline__ TexResult texture_descend(const Acc& acc, const Image
         TexRec T = acc.texrec(t);
         if (T.kind == B200RT_TEX_SOLID) { out.rgb = f3(T.r, T.g, T.b); return out; }   // solid.rs:17-21
         if (T.kind == B200RT_TEX_CHECKER) {                                              // checker.rs:28-36
-            // accurate sinf: sizes reach 8/r ~ 160 and coordinates ~ 30
-            float sn = sin_accurate(T.scalar * h.p.x) * sin_accurate(T.scalar * h.p.y) * sin_accurate(T.scalar * h.p.z);
-            t = sn < 0.0f ? T.odd : T.even;
+            t = checker_odd(T.scalar, h.p) ? T.odd : T.even;
             continue;
         }
         if (T.kind == B200RT_TEX_IMAGE) {                                                // image_texture.rs:34-56
