@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
         uint32_t depth = 0;
-        int node = B200RT_TRAV_DONE, sp = 1;
+        int node = B200RT_TRAV_DONE;
+        int* top_sp = stack + BLK;       // next free slot of this lane's stack column
         Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
         stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
 
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
                 c.t = INFINITY; c.code = -1; c.face = 0;
                 hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc, &inv_e);
-                node = 0; sp = 1; ++nrays;
+                node = 0; top_sp = stack + BLK; ++nrays;
             }
 
             // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
@@ -387,9 +388,9 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 //  18 lanes per step instead of 13, but 8 % slower overall — profiles/README.md)
                 while (node >= 0 && node != B200RT_TRAV_DONE) {
                     if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
-                    trav_inner_s<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                    trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK, T_MIN, c, node, tc);
                 }
-                if (node < 0) trav_leaf_s<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
+                if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLK, T_MIN, c, node, tc);
                 unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
                 if ((uint32_t)__popc(still) < a.trav_threshold) break;
             }

@@ -160,7 +160,8 @@ struct Rng {
     // rng.gen::<f64>() (core/math.rs:24) at 24-bit resolution
     __device__ __forceinline__ float gen() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
     // random_real(rng, -1, 1) = min + (max - min) * gen  (core/math.rs:23-25)
-    __device__ __forceinline__ float gen_pm1() { return fmaf(2.0f, gen(), -1.0f); }
+    // (2 g - 1 rounded once; (u >> 8) * 2^-23 - 1 in one FMA is the same value)
+    __device__ __forceinline__ float gen_pm1() { return fmaf((float)(next_u32() >> 8), 1.0f / 8388608.0f, -1.0f); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -467,11 +468,14 @@ __device__ __forceinline__ void trav_inner(const RayF& r, const Acc& acc, int* s
     }
 }
 
-// Variants for a stack whose element 0 holds B200RT_TRAV_DONE (sp starts at 1): a pop needs no
-// emptiness test, the sentinel ends the traversal.
+// Variants for the v2 render kernel.  The stack is addressed through a moving pointer
+// (`top` = next free slot of this lane's column) and its element 0 holds B200RT_TRAV_DONE, so a
+// pop needs neither an index multiply nor an emptiness test: the sentinel ends the traversal.
+// The step is written branch-free (selects + one predicated store / load): the three outcomes
+// (both children hit / one / none) otherwise diverge inside nearly every warp step.
 template <bool COUNT, bool FAST, class Acc>
-__device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, const Closest& c,
-                                             int& node, int& sp, TravCounters& tc) {
+__device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, int*& top, int stride, float t_min, const Closest& c,
+                                             int& node, TravCounters& tc) {
     float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
     if (COUNT) tc.nodes++;
     float e0, e1;
@@ -484,23 +488,22 @@ __device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, int*
         h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
     }
     int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-    if (h0 && h1) {
-        bool swap = e1 < e0;
-        stack[sp * stride] = swap ? c0 : c1; ++sp;
-        node = swap ? c1 : c0;
-    } else if (h0 || h1) {
-        node = h0 ? c0 : c1;
-    } else {
-        --sp; node = stack[sp * stride];
-    }
+    bool both = h0 && h1, none = !h0 && !h1;
+    bool take1 = h1 && (!h0 || e1 < e0);            // descend into child 1
+    int near_c = take1 ? c1 : c0, far_c = take1 ? c0 : c1;
+    if (both) *top = far_c;
+    top += both ? stride : 0;
+    top -= none ? stride : 0;
+    if (none) near_c = *top;
+    node = near_c;
 }
 
 template <bool COUNT, class Acc>
-__device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, Closest& c,
-                                            int& node, int& sp, TravCounters& tc) {
+__device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, int*& top, int stride, float t_min, Closest& c,
+                                            int& node, TravCounters& tc) {
     if (COUNT) tc.prims++;
     hit_leaf(r, acc, node, t_min, c);
-    --sp; node = stack[sp * stride];
+    top -= stride; node = *top;
 }
 
 template <bool COUNT, class Acc>
@@ -775,13 +778,13 @@ __device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h,
     out.scattered = true;
     if (m.kind == B200RT_MAT_DIELECTRIC) {                              // dielectric.rs:22-49
         float ir = m.m0.w;
-        float ratio = h.front ? 1.0f / ir : ir;
+        float ratio = h.front ? __fdividef(1.0f, ir) : ir;   // 2-ulp divide: IEEE `/` takes its slow path for ir = 1 (0 / 2 below)
         float3 ud = unit(r.d);
         float cos_theta = fminf(-dot(ud, h.n), 1.0f);
         float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
         bool reflect = ratio * sin_theta > 1.0f;
         if (!reflect) {                                                 // `||` short-circuit: no draw under TIR
-            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            float r0 = __fdividef(1.0f - ratio, 1.0f + ratio);
             r0 = r0 * r0;
             float k = 1.0f - cos_theta;
             float k2 = k * k;
