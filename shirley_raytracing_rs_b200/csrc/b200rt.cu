@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant
     }
 }
 
+constexpr uint32_t RAYQ_SLOTS = 64, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + stream, tile pixel
+
 // Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
 // result does not depend on which lane traced which sample, nor on scheduling or sharding.
 __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v) {
@@ -265,6 +267,9 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
     const unsigned lt = (1u << lane) - 1u;
     // per-warp fixed-point accumulators [32 pixels][3] behind the stack columns
     long long* wacc = reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (threadIdx.x >> 5) * 96;
+    // per-warp queue of generated primary rays, SoA [RAYQ_FIELDS][RAYQ_SLOTS] behind the accumulators
+    uint32_t* rayq = reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
+                     + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
     const TopPrims top = top_of(a.scene);
     const float T_MIN = 0.001f;                      // render.rs:31
     const bool has_perlin = a.scene.perlin != nullptr;
@@ -293,7 +298,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         const unsigned valid_mask = __ballot_sync(FULL, valid);
         const uint32_t nv = (uint32_t)__popc(valid_mask);
         const uint32_t n_items = a.samples * nv;
-        uint32_t next_item = 0;
+        uint32_t next_item = 0;          // next work-list item to generate
+        uint32_t q_head = 0, q_count = 0;  // the warp's ring of generated primary rays
         for (int k = lane; k < 96; k += 32) wacc[k] = 0;
         __syncwarp();
         uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
@@ -345,25 +351,52 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             if (done) { acc_add(wacc, pl, emit); alive = false; }
 
             // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
+            // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG
+            // keying, jitter, lens rejection loop, Camera::pixel_ray) and handed out to the ~6 lanes
+            // per iteration whose path ended; generating them on demand ran that code at 6 lanes.
             unsigned want_m = __ballot_sync(FULL, !alive);
-            uint32_t item = next_item + (uint32_t)__popc(want_m & lt);
-            bool regen = !alive && item < n_items;
-            next_item = min(n_items, next_item + (uint32_t)__popc(want_m));
+            const uint32_t want = (uint32_t)__popc(want_m);
+            if (q_count < want && next_item < n_items) {           // warp-uniform
+                __syncwarp();
+                uint32_t item = next_item + (uint32_t)lane;
+                if (item < n_items) {
+                    uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
+                    uint32_t kth = item - sidx * nv;
+                    uint32_t qpl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
+                    uint32_t px = px0 + (qpl & (TILE_W - 1)), py = py0 + (qpl >> 3);
+                    Rng qr;
+                    qr.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                    float jx = (float)px + qr.gen();
+                    float jy = (float)py + qr.gen();
+                    float3 qo, qd;
+                    pixel_ray(a.cam, qr, jx, jy, &qo, &qd);
+                    uint32_t slot = (q_head + q_count + (uint32_t)lane) & (RAYQ_SLOTS - 1);
+                    rayq[0 * RAYQ_SLOTS + slot] = __float_as_uint(qo.x); rayq[1 * RAYQ_SLOTS + slot] = __float_as_uint(qo.y);
+                    rayq[2 * RAYQ_SLOTS + slot] = __float_as_uint(qo.z); rayq[3 * RAYQ_SLOTS + slot] = __float_as_uint(qd.x);
+                    rayq[4 * RAYQ_SLOTS + slot] = __float_as_uint(qd.y); rayq[5 * RAYQ_SLOTS + slot] = __float_as_uint(qd.z);
+                    rayq[6 * RAYQ_SLOTS + slot] = qr.state; rayq[7 * RAYQ_SLOTS + slot] = qr.inc; rayq[8 * RAYQ_SLOTS + slot] = qpl;
+                }
+                uint32_t n_new = min(32u, n_items - next_item);
+                next_item += n_new; q_count += n_new;
+                __syncwarp();
+            }
+            const uint32_t rank = (uint32_t)__popc(want_m & lt);
+            bool regen = !alive && rank < q_count;
             if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
             if (regen) {
-                uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
-                uint32_t kth = item - sidx * nv;
-                pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
-                uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
-                rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
-                float jx = (float)px + rng.gen();
-                float jy = (float)py + rng.gen();
-                pixel_ray(a.cam, rng, jx, jy, &ray.o, &ray.d);
+                uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);
+                ray.o = f3(__uint_as_float(rayq[0 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[1 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[2 * RAYQ_SLOTS + slot]));
+                ray.d = f3(__uint_as_float(rayq[3 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[4 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[5 * RAYQ_SLOTS + slot]));
+                rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot]; pl = rayq[8 * RAYQ_SLOTS + slot];
                 atten = f3(1, 1, 1); emit = f3(0, 0, 0);
                 depth = a.max_depth;
                 alive = depth > 0;
                 setup = alive;
                 ++npaths;
+            }
+            {
+                uint32_t taken = min(want, q_count);
+                q_head = (q_head + taken) & (RAYQ_SLOTS - 1); q_count -= taken;
             }
             if (!__any_sync(FULL, alive)) break;
             if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
@@ -1180,7 +1213,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
 
     uint32_t target_blocks = (block_threads == 256 && kernel_version != 3) ? 2 : 1;
     size_t extra = kernel_version == 3 ? (size_t)(block_threads / 32) * pool_words(pool_slots) * 4
-                   : (kernel_version == 2 ? (size_t)(block_threads / 32) * 96 * sizeof(long long) : 0);
+                   : (kernel_version == 2 ? (size_t)(block_threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)) : 0);
     SmemPlan plan = make_plan(sc, target_blocks, block_threads, extra);
     if (!plan.all_in_smem && target_blocks > 1) { SmemPlan p1 = make_plan(sc, 1, block_threads, extra); if (p1.all_in_smem) plan = p1; }
     a.plan = plan;
