@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
             for (;;) {
                 if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
-                // (a warp-uniform inner loop that stops below a lane threshold was measured too:
-                //  18 lanes per step instead of 13, but 8 % slower overall — profiles/README.md)
+                // (a warp-uniform inner loop that stops below a lane threshold was measured twice:
+                //  15-18 lanes per step instead of 13, but 2-5 % slower overall — profiles/README.md)
                 while (node >= 0 && node != B200RT_TRAV_DONE) {
                     if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
                     trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK, T_MIN, c, node, tc);
@@ -1199,7 +1199,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     int block_threads = env_int("B200RT_BLOCK", 768);
     if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
     if (kernel_version == 1) block_threads = BLOCK;
-    a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 4)));
+    a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 8)));
     a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
     a.wf_fetch = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_FETCH", 8)));
     a.wf_park = (uint32_t)std::min(33, std::max(0, env_int("B200RT_WF_PARK", 33)));
