@@ -36,9 +36,14 @@ void b200rt_host_scene_destroy(B200rtHostScene* scene);
 const B200rtSceneDesc* b200rt_host_scene_desc(const B200rtHostScene* scene);
 
 /* Decoded RGB8 pixels for TextureLoader::EarthBuiltin (name "EarthBuiltin") or
- * ImagePath(name) (image_texture.rs:18-31). Without a registration EarthBuiltin falls back
- * to a procedural 1024x512 stand-in; ImagePath fails like image::open. */
+ * ImagePath(name) (image_texture.rs:18-31); a registration takes precedence over decoding. */
 int  b200rt_host_register_image(const char* name, uint32_t width, uint32_t height, const uint8_t* rgb8);
+/* image::load_from_memory for a baseline JPEG (image_texture.rs:18-21,28-31): RGB8 pixels, top row
+ * first, in a buffer to release with b200rt_free.  ImagePath textures that were not registered
+ * are decoded with the same routine at finalize; EarthBuiltin is decoded from the file named by
+ * the environment variable B200RT_EARTHMAP (a copy of the reference's assets/earthmap.jpg) when
+ * set, else it is the procedural stand-in. */
+int  b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint8_t** rgb8);
 
 /* CameraBuilder + CameraPosition::look_at (camera/mod.rs:23-85).  aperture < 0 = None;
  * focus_length <= 0 keeps look_at's |camera - target|.  Exactly two of

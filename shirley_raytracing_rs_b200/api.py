@@ -259,6 +259,17 @@ def register_image(name: str, rgb: np.ndarray) -> None:
     F.check(lib.b200rt_host_register_image(name.encode(), w, h, rgb.ctypes.data), host=True)
 
 
+def decode_jpeg(data: bytes) -> np.ndarray:
+    """image::load_from_memory for a baseline JPEG (image_texture.rs:18-21): (H, W, 3) uint8."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    w, h, out = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    F.check(lib.b200rt_host_decode_jpeg(buf, len(data), C.byref(w), C.byref(h), C.byref(out)), host=True)
+    try:
+        return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 3)).copy()
+    finally:
+        lib.b200rt_free(out)
+
+
 # ---- camera (camera/mod.rs) -------------------------------------------------------------------------
 def camera(look_from, look_at, up=(0.0, 1.0, 0.0), *, vfov=20.0, focal_length=1.0, aperture: Optional[float] = 0.001,
            width: int = 0, height: int = 0, aspect_ratio=(3, 2), focus_length: float = 0.0) -> F.Camera:

@@ -82,6 +82,19 @@ int b200rt_host_register_image(const char* name, uint32_t width, uint32_t height
     return B200RT_OK;
 }
 
+int b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint8_t** rgb8) {
+    if (!data || !width || !height || !rgb8) return host_fail(B200RT_EINVAL, "NULL argument");
+    *rgb8 = nullptr;
+    try {
+        scene::ImageData img = scene::decode_jpeg(data, size);
+        uint8_t* buf = (uint8_t*)malloc(img.rgb.size() ? img.rgb.size() : 1);
+        if (!buf) return host_fail(B200RT_ENOMEM, "out of memory");
+        memcpy(buf, img.rgb.data(), img.rgb.size());
+        *width = img.width; *height = img.height; *rgb8 = buf;
+        return B200RT_OK;
+    } catch (const std::exception& e) { return host_fail(B200RT_EINVAL, e.what()); }
+}
+
 int b200rt_host_camera(const double from[3], const double at[3], const double up[3], double vfov, double focal_length, double aperture,
                        uint32_t image_width, uint32_t image_height, uint32_t ratio_num, uint32_t ratio_den, double focus_length, B200rtCamera* out) {
     if (!from || !at || !up || !out) return host_fail(B200RT_EINVAL, "NULL argument");

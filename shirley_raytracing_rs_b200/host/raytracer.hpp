@@ -120,6 +120,10 @@ struct ImageData { uint32_t width = 0, height = 0; std::vector<uint8_t> rgb; };
 void register_image(const std::string& name, ImageData img);
 bool lookup_image(const std::string& name, ImageData* out);
 ImageData synthetic_earth(uint32_t width = 1024, uint32_t height = 512);   // stand-in of the same shape as earthmap.jpg
+// Baseline JPEG -> RGB8 (jpeg_decoder.cpp), what `image::open` / `load_from_memory` do for the
+// reference's textures (image_texture.rs:18-31).  Throw Error on malformed or unsupported files.
+ImageData decode_jpeg(const uint8_t* data, size_t size);
+ImageData load_jpeg_file(const std::string& path);
 
 // The flattened scene: owns the SoA arrays `desc` points into.
 struct Scene {

@@ -4,6 +4,8 @@
 #include <mutex>
 #include <sstream>
 
+#include <cstdlib>
+
 #include "raytracer.hpp"
 
 namespace raytracer {
@@ -122,8 +124,15 @@ struct TextureManager {   // loader.rs:108-131
                 std::string name = t.kind == TextureLoader::EarthBuiltin ? "EarthBuiltin" : t.path;
                 ImageData img;
                 if (!lookup_image(name, &img)) {
-                    if (t.kind == TextureLoader::EarthBuiltin) img = synthetic_earth();
-                    else throw Error("image texture `" + name + "` is not registered (b200rt_host_register_image) — image::open failed");   // image_texture.rs:24
+                    if (t.kind == TextureLoader::EarthBuiltin) {
+                        // the reference embeds assets/earthmap.jpg (image_texture.rs:11); that file is not part of
+                        // this repository: decode it when the host points at a copy, else the procedural stand-in
+                        const char* env = getenv("B200RT_EARTHMAP");
+                        if (env && *env) img = load_jpeg_file(env);
+                        else img = synthetic_earth();
+                    } else {
+                        img = load_jpeg_file(t.path);   // image_texture.rs:23-26 `image::open(path)?` (baseline JPEG only here)
+                    }
                 }
                 x.kind = B200RT_TEX_IMAGE; x.image = (int32_t)sc.image_store.size();
                 sc.image_store.push_back(std::move(img));
