@@ -25,9 +25,12 @@ per-pixel sums land in a float4 accumulation buffer.  A "ray" is one closest-hit
 
 Multi-GPU (N > 1, one rank per GPU under torchrun): sample-range sharding — every rank
 renders the full frame with its own `spp` samples (sample_offset = rank * spp; streams are
-keyed by (pixel, sample) so the union is one N*spp-sample frame) and the accumulation
-buffers are summed onto rank 0 with one NCCL reduce per frame, inside the timed region.
-Per-GPU work is fixed: "scaling": "weak".
+keyed by (pixel, sample) so the union is one N*spp-sample frame).  The per-rank buffers
+become one RGB8 frame on rank 0 inside the timed region: by default with the fused
+peer-memory kernel (b200rt_resolve_peers_rgb8_device: every rank sums its band of rows from
+all ranks' buffers over NVLink P2P, resolves and stores the bytes into rank 0's frame;
+`--combine nccl` = one NCCL reduce + resolve on rank 0 instead).  Per-GPU work is fixed:
+"scaling": "weak".
 
 `--impl reference` times the reference's own CPU path (the oracle port — the Rust crate
 cannot be built in this image) on the same config with all host threads.
@@ -47,6 +50,12 @@ sys.path.insert(0, ROOT)
 WIDTH, SPP, DEPTH, SCENE_SEED = 1200, 500, 50, 0xDEADBEEF
 WORKLOAD = "weekend_final_scene_1200x800_500spp_depth50"
 METRIC = "Mrays/s, Weekend final scene 1200x800 500spp (ms/frame in ms_per_step)"
+
+
+# stdout carries exactly ONE JSON line: anything else a library prints there (NCCL's version banner,
+# for one) is redirected to stderr.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 
 def log(*a):
@@ -134,7 +143,7 @@ def run_reference(args, rank, world):
             "config": {"workload": WORKLOAD, "scene_seed": SCENE_SEED, "sample": sample, "rays_per_step": rays // max(1, args.steps)},
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -148,6 +157,8 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of the bounded CPU sample per step")
     ap.add_argument("--cpu-baseline-spp", type=int, default=128, help="bounded CPU sample: ~10-30 s of host work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--combine", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused peer-memory reduce+resolve kernel over NVLink (default) or NCCL reduce then resolve on rank 0")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,21 +191,35 @@ def main():
     info = scene.info(local_rank)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
-    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    peer = None
+    if world > 1 and args.combine == "peer":
+        from shirley_raytracing_rs_b200.sharding import PeerFrame
+        peer = PeerFrame(W, H, local_rank)               # IPC-shared accumulation buffers + the frame on rank 0
+        accum = peer.accum()
+    else:
+        accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    frame_dev = torch.empty((H, W, 3), dtype=torch.uint8, device=dev) if (world > 1 and peer is None and rank == 0) else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def params(step, count=False):
         return F.RenderParams(samples=args.spp, sample_offset=rank * args.spp, max_depth=DEPTH,
                               flags=F.FLAG_COUNT_TRAVERSAL if count else 0, seed=77 + step, device=-1)
 
+    def combine(scene_handle=None):
+        """N > 1: the per-rank buffers become ONE RGB8 frame on rank 0."""
+        if peer is not None:
+            peer.combine(args.spp * world, sptr)          # barrier, fused sum+resolve of this rank's row band into rank 0's frame, barrier
+        else:
+            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                F.check(lib.b200rt_resolve_rgb8_device(accum.data_ptr(), W, H, args.spp * world, frame_dev.data_ptr(), sptr))
+
     def frame(step, count=False):
-        """One step with the scene resident in HBM: render (+ NCCL sum onto rank 0)."""
+        """One step with the scene resident in HBM: render (+ at N > 1 the cross-GPU sum and resolve)."""
         p = params(step, count)
         F.check(lib.b200rt_render_device(dscene, C.byref(cam), C.byref(p), accum.data_ptr(), sptr))
         if world > 1:
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-        st = F.Stats()
-        return st
+            combine()
 
     def finish():
         st = F.Stats()
@@ -233,6 +258,8 @@ def main():
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1)); kernel_ms.append(st.kernel_ms)
         rays += st.rays; launches += st.launches
+        if world > 1:
+            launches += 1 if (peer is not None or rank == 0) else 0   # resolve_peers_kernel on every rank / resolve_kernel on rank 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -260,12 +287,10 @@ def main():
             else:
                 p = params(step)
                 F.check(lib.b200rt_render_device(h, C.byref(cam), C.byref(p), accum.data_ptr(), sptr))
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                combine()
                 F.check(lib.b200rt_render_device_finish(h, sptr, C.byref(st)))
                 if rank == 0:
-                    out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-                    F.check(lib.b200rt_resolve_rgb8_device(accum.data_ptr(), W, H, args.spp * world, out.data_ptr(), sptr))
-                    rgb_t.copy_(out, non_blocking=True)
+                    rgb_t.copy_(peer.frame() if peer is not None else frame_dev, non_blocking=True)
                 torch.cuda.synchronize()
         finally:
             lib.b200rt_scene_destroy(h)
@@ -321,7 +346,7 @@ def main():
                 "config": {"workload": WORKLOAD if (args.spp == SPP and args.width == WIDTH) else f"weekend_{W}x{H}_{args.spp}spp_depth{DEPTH}",
                            "scene": "src/scenes.rs random_scene (day), seeded", "scene_seed": SCENE_SEED, "objects": int(info.n_prims),
                            "bvh_nodes": int(info.n_bvh_nodes), "image": [W, H], "spp_per_gpu": args.spp, "max_depth": DEPTH,
-                           "parallelism": f"sample-range x{world}" if world > 1 else "single GPU",
+                           "parallelism": (f"sample-range x{world}, " + ("fused peer-memory sum+resolve (NVLink P2P)" if peer is not None else "NCCL reduce + resolve on rank 0")) if world > 1 else "single GPU",
                            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events)",
                            "rays_per_step": rays_all / args.steps, "Msamples_per_s": (W * H * args.spp * world) / (total_ms / args.steps * 1e-3) / 1e6},
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
@@ -337,7 +362,9 @@ def main():
             line["cpu_baseline"] = {"value": ost.rays / ost.seconds / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                     "sample": f"{W}x{H} full frame at {args.cpu_baseline_spp} spp (of {args.spp}), f64 oracle, OpenMP dynamic,1 over scanlines, {ost.seconds:.1f} s",
                                     "pops_per_ray": ost.pops / ost.rays, "leaf_tests_per_ray": ost.leaf_tests / ost.rays}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -251,6 +251,27 @@ int  b200rt_resolve_rgb8(const float* accum, uint32_t width, uint32_t height, ui
 int  b200rt_resolve_rgb8_device(const float* d_accum, uint32_t width, uint32_t height,
                                 uint32_t samples, uint8_t* d_out_rgb8, void* cuda_stream);
 
+/* Multi-GPU, one process per GPU: the cross-GPU sum of sample-range-sharded
+ * accumulation buffers FUSED into to_image's resolve (image.rs:34-40).  Every process creates
+ * its accumulation buffer with b200rt_peer_buffer_create (cudaMalloc + an IPC handle, 64 opaque
+ * bytes the host exchanges however it likes, e.g. torch.distributed.all_gather_object), opens
+ * the other ranks' handles, renders into its own buffer (b200rt_render_device), synchronises
+ * the ranks' streams (a barrier), and then resolves a band of rows [row_begin, row_end) from
+ * ALL buffers at once: out[(H-1-j)*W + i] = sat_u8(sqrt(sum_r accum_r[j][i].rgb / n) * 255.999),
+ * summed in the order given (deterministic bytes).  d_out_rgb8 is the W*H*3 frame — normally a
+ * peer pointer to the root rank's frame buffer, so the bands of all ranks assemble there over
+ * NVLink without an intermediate reduced float buffer.  n = `samples` (total over ranks), or
+ * the summed .w when samples == 0.  (0, 0) selects all rows. */
+#define B200RT_PEER_HANDLE_BYTES 64
+int  b200rt_peer_buffer_create(int device, size_t bytes, void** d_ptr, uint8_t handle[B200RT_PEER_HANDLE_BYTES]);
+int  b200rt_peer_buffer_open(int device, const uint8_t handle[B200RT_PEER_HANDLE_BYTES], void** d_ptr);
+int  b200rt_peer_buffer_close(int device, void* d_ptr);      /* a pointer from _open  */
+int  b200rt_peer_buffer_destroy(int device, void* d_ptr);    /* a pointer from _create */
+int  b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers,
+                                      uint32_t width, uint32_t height, uint32_t samples,
+                                      uint32_t row_begin, uint32_t row_end,
+                                      uint8_t* d_out_rgb8, void* cuda_stream);
+
 /* Replaces RgbImage::save_with_format(.., Png) (image.rs:42): 8-bit RGB PNG via zlib. */
 int  b200rt_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);
 /* Same encoder into a malloc'ed buffer; release with b200rt_free. */

@@ -127,6 +127,12 @@ SIGNATURES = {
     "b200rt_render_device_finish": (C.c_int, [C.c_void_p, C.c_void_p, _P(Stats)]),
     "b200rt_resolve_rgb8": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     "b200rt_resolve_rgb8_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200rt_peer_buffer_create": (C.c_int, [C.c_int, C.c_size_t, _P(C.c_void_p), C.c_void_p]),
+    "b200rt_peer_buffer_open": (C.c_int, [C.c_int, C.c_void_p, _P(C.c_void_p)]),
+    "b200rt_peer_buffer_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "b200rt_peer_buffer_destroy": (C.c_int, [C.c_int, C.c_void_p]),
+    "b200rt_resolve_peers_rgb8_device": (C.c_int, [_P(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_void_p, C.c_void_p]),
     "b200rt_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "b200rt_encode_png": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_void_p), _P(C.c_size_t)]),
     "b200rt_free": (None, [C.c_void_p]),

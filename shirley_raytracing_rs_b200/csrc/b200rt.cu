@@ -883,6 +883,56 @@ __global__ void resolve_kernel(const float4* __restrict__ accum, uint32_t W, uin
     px[2] = to_pixel(sqrt((double)c.z * inv));
 }
 
+
+// K3p: the cross-GPU sum fused into the resolve.  With sample-range sharding
+// every GPU holds a full-frame float4 buffer of its own samples; instead of an NCCL reduce onto
+// one GPU followed by resolve_kernel there, each GPU takes a band of rows, reads that band from
+// EVERY GPU's buffer through NVLink peer pointers (coalesced 16-byte loads), adds them in rank
+// order (so the bytes do not depend on timing), applies to_image's arithmetic and stores the
+// RGB8 band — through a peer pointer again — into the frame on the root GPU.  One pass, no
+// intermediate reduced buffer, and the traffic is spread over all GPUs' links.
+constexpr int MAX_PEERS = 16;
+struct PeerResolveArgs {
+    const float4* accum[MAX_PEERS];
+    uint32_t n_peers, W, H, samples, row_begin, row_end;
+    uint8_t* out;
+};
+__device__ __forceinline__ float4 peer_sum(const PeerResolveArgs& a, size_t idx) {
+    float4 c = __ldcg(a.accum[0] + idx);        // .cg: peer data must not be served from a stale L1 line
+    for (uint32_t r = 1; r < a.n_peers; ++r) {
+        float4 v = __ldcg(a.accum[r] + idx);
+        c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
+    return c;
+}
+__global__ void resolve_peers_kernel(const __grid_constant__ PeerResolveArgs a) {
+    const uint32_t j = a.row_begin + blockIdx.y;
+    if (j >= a.row_end) return;
+    const uint32_t groups = (a.W + 3) / 4;
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    const uint32_t i0 = g * 4;
+    uint8_t bytes[12];
+    uint32_t n_px = min(4u, a.W - i0);
+    for (uint32_t k = 0; k < n_px; ++k) {
+        float4 c = peer_sum(a, (size_t)j * a.W + i0 + k);
+        double n = a.samples ? (double)a.samples : (double)c.w;
+        double inv = 1.0 / n;
+        bytes[3 * k + 0] = to_pixel(sqrt((double)c.x * inv));
+        bytes[3 * k + 1] = to_pixel(sqrt((double)c.y * inv));
+        bytes[3 * k + 2] = to_pixel(sqrt((double)c.z * inv));
+    }
+    uint8_t* px = a.out + ((size_t)(a.H - 1 - j) * a.W + i0) * 3;
+    if (n_px == 4 && ((uintptr_t)px & 3u) == 0) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(px);
+        w[0] = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
+        w[1] = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | ((uint32_t)bytes[7] << 24);
+        w[2] = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | ((uint32_t)bytes[11] << 24);
+    } else {
+        for (uint32_t k = 0; k < 3 * n_px; ++k) px[k] = bytes[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // parity-hook kernels
 // ------------------------------------------------------------------------------------------
@@ -1569,6 +1619,69 @@ int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uin
     if (!d_accum || !d_out || W == 0 || H == 0) return fail(B200RT_EINVAL, "bad argument");
     dim3 block(128, 1), grid((W + 127) / 128, H);
     resolve_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(reinterpret_cast<const float4*>(d_accum), W, H, samples, d_out);
+    CU(cudaGetLastError());
+    return B200RT_OK;
+}
+
+// ---- peer-memory buffers for the fused cross-GPU resolve -------------------------------------
+int b200rt_peer_buffer_create(int device, size_t bytes, void** d_ptr, uint8_t handle[B200RT_PEER_HANDLE_BYTES]) {
+    if (!d_ptr || !handle || bytes == 0) return fail(B200RT_EINVAL, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= B200RT_PEER_HANDLE_BYTES, "handle size");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(B200RT_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memset(handle, 0, B200RT_PEER_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    CU(cudaMemset(p, 0, bytes));
+    *d_ptr = p;
+    return B200RT_OK;
+}
+int b200rt_peer_buffer_open(int device, const uint8_t handle[B200RT_PEER_HANDLE_BYTES], void** d_ptr) {
+    if (!d_ptr || !handle) return fail(B200RT_EINVAL, "bad argument");
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(B200RT_ECUDA, "cudaIpcOpenMemHandle (is peer access between the GPUs available?): %s", cudaGetErrorString(e));
+    *d_ptr = p;
+    return B200RT_OK;
+}
+int b200rt_peer_buffer_close(int device, void* d_ptr) {
+    if (!d_ptr) return B200RT_OK;
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return B200RT_OK;
+}
+int b200rt_peer_buffer_destroy(int device, void* d_ptr) {
+    if (!d_ptr) return B200RT_OK;
+    int rc = resolve_device(device, &device); if (rc) return rc;
+    DeviceGuard guard(device);
+    CU(cudaFree(d_ptr));
+    return B200RT_OK;
+}
+
+int b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers, uint32_t W, uint32_t H, uint32_t samples,
+                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, void* cuda_stream) {
+    if (!d_accums || !d_out || W == 0 || H == 0) return fail(B200RT_EINVAL, "bad argument");
+    if (n_peers < 1 || n_peers > (uint32_t)MAX_PEERS) return fail(B200RT_EINVAL, "n_peers %u outside [1, %d]", n_peers, MAX_PEERS);
+    if (row_begin == 0 && row_end == 0) row_end = H;
+    if (row_end > H || row_begin > row_end) return fail(B200RT_EINVAL, "row range [%u,%u) outside image height %u", row_begin, row_end, H);
+    if (row_begin == row_end) return B200RT_OK;
+    PeerResolveArgs a{};
+    for (uint32_t r = 0; r < n_peers; ++r) {
+        if (!d_accums[r]) return fail(B200RT_EINVAL, "accumulation buffer %u is NULL", r);
+        a.accum[r] = reinterpret_cast<const float4*>(d_accums[r]);
+    }
+    a.n_peers = n_peers; a.W = W; a.H = H; a.samples = samples; a.row_begin = row_begin; a.row_end = row_end; a.out = d_out;
+    dim3 block(128, 1), grid(((W + 3) / 4 + 127) / 128, row_end - row_begin);
+    resolve_peers_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(a);
     CU(cudaGetLastError());
     return B200RT_OK;
 }

@@ -51,3 +51,94 @@ def reduce_accum(accum, dst: int = 0):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
+
+
+def row_bands(height: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous row bands [begin, end), one per rank, for the fused cross-GPU resolve."""
+    if world < 1 or height < 0:
+        raise ValueError("world >= 1 and height >= 0 required")
+    return [(r * height // world, (r + 1) * height // world) for r in range(world)]
+
+
+class _DevicePtr:
+    """A raw device allocation seen through __cuda_array_interface__ (torch.as_tensor accepts it)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerFrame:
+    """Per-rank accumulation buffers visible to every rank of one node (CUDA IPC over NVLink)
+    plus the RGB8 frame on `root`, for b200rt_resolve_peers_rgb8_device: the cross-GPU sum is
+    fused into the resolve and every rank assembles its band of rows directly into the root's
+    frame (include/b200rt.h).  One process per GPU; handles travel over torch.distributed.
+
+        pf = PeerFrame(W, H, device_index)
+        render into pf.accum_ptr ...; pf.combine(total_samples, stream_ptr)   # collective
+        frame = pf.frame()          # on root: (H, W, 3) uint8 torch tensor on the device
+    """
+
+    def __init__(self, width: int, height: int, device: int, root: int = 0, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _ffi as F
+        self._F, self._C, self._torch, self._dist = F, C, torch, dist
+        self.W, self.H, self.device, self.root, self.group = width, height, device, root, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("at most 16 peers")
+        lib = F.lib
+        self._own = []
+        def create(nbytes):
+            p, h = C.c_void_p(), (C.c_uint8 * 64)()
+            F.check(lib.b200rt_peer_buffer_create(device, nbytes, C.byref(p), h))
+            self._own.append(p)
+            return p, bytes(h)
+        acc_p, acc_h = create(width * height * 16)
+        rgb_p, rgb_h = create(width * height * 3) if self.rank == root else (None, None)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (acc_h, rgb_h), group=group)
+        self._opened = []
+        def open_(h):
+            p, buf = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(h)
+            F.check(lib.b200rt_peer_buffer_open(device, buf, C.byref(p)))
+            self._opened.append(p)
+            return p
+        self.accum_ptrs = [acc_p if r == self.rank else open_(handles[r][0]) for r in range(self.world)]
+        self.frame_ptr = rgb_p if self.rank == root else open_(handles[root][1])
+        self.accum_ptr = acc_p
+        self._ptr_array = (C.c_void_p * self.world)(*[p.value for p in self.accum_ptrs])
+        self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device))
+        self.band = row_bands(height, self.world)[self.rank]
+
+    def sync(self):
+        """Stream-ordered barrier: kernels enqueued after it start after every rank's earlier work."""
+        self._dist.all_reduce(self._flag, group=self.group)
+
+    def combine(self, total_samples: int, stream_ptr=None):
+        """sync; resolve this rank's band from all ranks' buffers into the root's frame; sync."""
+        F, C = self._F, self._C
+        self.sync()
+        F.check(F.lib.b200rt_resolve_peers_rgb8_device(self._ptr_array, self.world, self.W, self.H, total_samples,
+                                                      self.band[0], self.band[1], self.frame_ptr, stream_ptr))
+        self.sync()
+
+    def accum(self):
+        """This rank's accumulation buffer as an (H, W, 4) float32 torch tensor (no copy)."""
+        return self._torch.as_tensor(_DevicePtr(self.accum_ptr.value, (self.H, self.W, 4), "<f4"), device=self._torch.device("cuda", self.device))
+
+    def frame(self):
+        """The assembled RGB8 frame, (H, W, 3) uint8, top row first (valid on every rank as a peer view)."""
+        return self._torch.as_tensor(_DevicePtr(self.frame_ptr.value, (self.H, self.W, 3), "|u1"), device=self._torch.device("cuda", self.device))
+
+    def close(self):
+        F = self._F
+        self._torch.cuda.synchronize()
+        self._dist.barrier(group=self.group)          # nobody may still be reading a buffer about to be freed
+        for p in self._opened:
+            F.check(F.lib.b200rt_peer_buffer_close(self.device, p))
+        self._dist.barrier(group=self.group)
+        for p in self._own:
+            F.check(F.lib.b200rt_peer_buffer_destroy(self.device, p))
+        self._opened, self._own = [], []

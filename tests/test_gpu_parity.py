@@ -358,3 +358,33 @@ def test_max_depth_semantics(rt, po, gpu_required):
     sky = (o1.sum(axis=2) > 0)
     assert abs(sky.mean() - (g1[..., :3].sum(axis=2) > 0).mean()) < 0.01
     np.testing.assert_allclose(g1[..., :3][sky].mean(), o1[sky].mean(), rtol=2e-3)
+
+
+# ---- K3p fused cross-GPU sum + resolve (single-device form: the peer pointers are local) -------------------
+def test_resolve_peers_equals_sum_then_resolve(rt, gpu_required):
+    import ctypes as C
+    import torch
+    F = rt._ffi
+    rng = np.random.default_rng(11)
+    H, W, n = 37, 53, 3                                   # W % 4 != 0: exercises the byte-wise tail
+    for W in (53, 64):
+        bufs = [torch.from_numpy(rng.uniform(0, 40, size=(H, W, 4)).astype(np.float32)).cuda() for _ in range(n)]
+        for b in bufs:
+            b[..., 3] = 20.0
+        ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in bufs])
+        out = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
+        # two row bands, like two ranks would
+        for band in ((0, 20), (20, H)):
+            F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 60, band[0], band[1], out.data_ptr(), None))
+        torch.cuda.synchronize()
+        total = bufs[0].clone()
+        for b in bufs[1:]:
+            total += b                                     # same order, same f32 adds
+        want = rt.resolve_rgb8(total.cpu().numpy(), samples=60)
+        assert np.array_equal(out.cpu().numpy(), want)
+        # samples == 0: n comes from the summed .w
+        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 0, 0, 0, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want)
+    with pytest.raises(rt.B200rtError):
+        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, 17, W, H, 60, 0, 0, out.data_ptr(), None))

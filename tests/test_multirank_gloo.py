@@ -61,6 +61,11 @@ def test_sample_range_plan():
     assert sharding.tile_shard(4, 2) == (4, 2)
     with pytest.raises(ValueError):
         sharding.tile_shard(2, 2)
+    bands = sharding.row_bands(800, 8)                      # fused cross-GPU resolve: one band of rows per rank
+    assert bands[0] == (0, 100) and bands[-1] == (700, 800)
+    for H, n in ((7, 4), (1, 8), (1080, 3)):
+        b = sharding.row_bands(H, n)
+        assert b[0][0] == 0 and b[-1][1] == H and all(b[i][1] == b[i + 1][0] for i in range(n - 1))
 
 
 def test_two_rank_sample_sharding_matches_single_process(tmp_path, rt, po):
