@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
         uint32_t depth = 0;
         int node = B200RT_TRAV_DONE;
-        int* top_sp = stack + BLK;       // next free slot of this lane's stack column
+        const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
+        uint32_t top_sp = stack_s + BLK * 4;   // shared-window address of the next free slot of this lane's stack column
         Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
         stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
 
@@ -411,19 +412,19 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
                 c.t = INFINITY; c.code = -1; c.face = 0;
                 hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc, &inv_e);
-                node = 0; top_sp = stack + BLK; ++nrays;
+                node = 0; top_sp = stack_s + BLK * 4; ++nrays;
             }
 
             // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
             for (;;) {
                 if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
-                // (a warp-uniform inner loop that stops below a lane threshold was measured twice:
-                //  15-18 lanes per step instead of 13, but 2-5 % slower overall — profiles/README.md)
+                // (a warp-uniform inner loop that stops below a lane threshold, and a cap on the steps per
+                //  round, were measured: 15-18 lanes per step instead of 13.6, but no faster — profiles/README.md)
                 while (node >= 0 && node != B200RT_TRAV_DONE) {
                     if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
-                    trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK, T_MIN, c, node, tc);
+                    trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
                 }
-                if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLK, T_MIN, c, node, tc);
+                if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
                 unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
                 if ((uint32_t)__popc(still) < a.trav_threshold) break;
             }
@@ -1290,6 +1291,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         return B200RT_OK;
     };
     int rc;
+    if (kernel_version == 2 && fast) a.scene.nodes = sc->ds.cnodes;   // centre/half-extent boxes for aabb_center
 #ifdef B200RT_DEV_BUILD
     // `make DEV=1`: only the default variant, for fast edit-compile-measure loops
     if (kernel_version != 2) return fail(B200RT_EINVAL, "dev build: only B200RT_KERNEL=2 is compiled");
@@ -1476,8 +1478,31 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     static_assert(sizeof(HostNode) == sizeof(BvhNode), "node layout");
     std::vector<BvhNode> nodes(bvh.nodes.size());
     memcpy(nodes.data(), bvh.nodes.data(), nodes.size() * sizeof(BvhNode));
+    // The render kernel's copy of the tree: the same nodes with each child box as centre +
+    // half-extent (rt_device.cuh: aabb_center).  The box is re-derived outwards: c = (lo+hi)/2,
+    // h = max(hi - c, c - lo) bumped up one ulp, so [c - h, c + h] contains [lo, hi].  An empty
+    // child (lo > hi) gets h = -1: near > far on every axis, never entered.
+    std::vector<BvhNode> cnodes(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const float* q = reinterpret_cast<const float*>(&nodes[i]);
+        float* o = reinterpret_cast<float*>(&cnodes[i]);
+        for (int ch = 0; ch < 2; ++ch) {
+            const float* lo = q + 6 * ch; const float* hi = lo + 3;
+            for (int k = 0; k < 3; ++k) {
+                float c = 0.f, h = -1.f;
+                if (lo[k] <= hi[k]) {
+                    c = 0.5f * lo[k] + 0.5f * hi[k];
+                    h = std::nextafterf(std::max(hi[k] - c, c - lo[k]), INFINITY);
+                    if (!std::isfinite(c) || !std::isfinite(h)) { c = 0.f; h = 3.0e38f; }   // unbounded box: always entered
+                }
+                o[6 * ch + k] = c; o[6 * ch + 3 + k] = h;
+            }
+        }
+        o[12] = q[12]; o[13] = q[13]; o[14] = q[14]; o[15] = q[15];
+    }
     Arena arena;
     size_t off_nodes = arena.put(nodes), off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
+    size_t off_cnodes = arena.put(cnodes);
     // images: RGB8 -> RGBA8 so a texel is one 4-byte load
     std::vector<ImageRec> images(d->n_images);
     std::vector<size_t> off_img(d->n_images);
@@ -1508,6 +1533,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         sc->info.device_bytes = arena.host.size();
     }
     sc->ds.nodes = reinterpret_cast<const BvhNode*>(dbase + off_nodes);
+    sc->ds.cnodes = reinterpret_cast<const BvhNode*>(dbase + off_cnodes);
     sc->ds.geom = reinterpret_cast<const GeomRec*>(dbase + off_geom);
     sc->ds.mats = reinterpret_cast<const MatRec*>(dbase + off_mats);
     sc->ds.tex = reinterpret_cast<const TexRec*>(dbase + off_tex);

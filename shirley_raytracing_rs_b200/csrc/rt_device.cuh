@@ -47,6 +47,7 @@ struct PerlinRec { float4 ranfloat[256]; uint8_t perm_x[256], perm_y[256], perm_
 
 struct DeviceScene {
     const BvhNode* nodes;
+    const BvhNode* cnodes;      // same tree, child boxes as (centre.xyz, half.xyz): the render kernel's slab test
     const GeomRec* geom;
     const MatRec* mats;
     const TexRec* tex;
@@ -248,6 +249,22 @@ __device__ __forceinline__ bool aabb_fast(const RayF& r, float lox, float loy, f
     float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_max));
     *t_enter = lo;
     return lo <= hi;
+}
+
+// Slab test on a box given as centre + half-extent (DeviceScene::cnodes): per axis
+//   t_c = c * inv - o * inv,   t_near = t_c - h |inv|,   t_far = t_c + h |inv|
+// — three FMAs and no min/max pair.  ncu on the min/max form: the ALU pipe (FMNMX, selects,
+// integer ops; half the FMA pipes' rate on sm_100) was 58 % busy against 23 % for the FMA pipes,
+// with 10 ALU-pipe operations per box; this form has 4.  Error analysis as for aabb_fast plus
+// eps * |c| for the centre: covered by the same box padding (scene_create).
+__device__ __forceinline__ void aabb_center(const RayF& r, float cx, float cy, float cz, float hx, float hy, float hz,
+                                            float t_min, float t_max, float* lo, float* hi) {
+    float tx = fmaf(cx, r.inv.x, -r.ood.x), ty = fmaf(cy, r.inv.y, -r.ood.y), tz = fmaf(cz, r.inv.z, -r.ood.z);
+    float ax = fabsf(r.inv.x), ay = fabsf(r.inv.y), az = fabsf(r.inv.z);      // |x| is an operand modifier of FFMA
+    float nx = fmaf(-hx, ax, tx), ny = fmaf(-hy, ay, ty), nz = fmaf(-hz, az, tz);
+    float fx = fmaf(hx, ax, tx), fy = fmaf(hy, ay, ty), fz = fmaf(hz, az, tz);
+    *lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_min));
+    *hi = fminf(fminf(fx, fy), fminf(fz, t_max));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -474,36 +491,58 @@ __device__ __forceinline__ void trav_inner(const RayF& r, const Acc& acc, int* s
 // The step is written branch-free (selects + one predicated store / load): the three outcomes
 // (both children hit / one / none) otherwise diverge inside nearly every warp step.
 template <bool COUNT, bool FAST, class Acc>
-__device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, int*& top, int stride, float t_min, const Closest& c,
+__device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, uint32_t& top, int stride_bytes, float t_min, const Closest& c,
                                              int& node, TravCounters& tc) {
     float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
     if (COUNT) tc.nodes++;
-    float e0, e1;
-    bool h0, h1;
-    if (FAST) {
-        h0 = aabb_fast(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
-        h1 = aabb_fast(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+    float lo0, hi0, lo1, hi1;
+    if (FAST) {   // `nodes` is the centre/half-extent copy (DeviceScene::cnodes)
+        aabb_center(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &lo0, &hi0);
+        aabb_center(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &lo1, &hi1);
     } else {
-        h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
-        h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
+        // aabb_hit2's verdict as an interval: a miss becomes an empty one
+        bool h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &lo0);
+        bool h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &lo1);
+        hi0 = h0 ? INFINITY : -INFINITY; hi1 = h1 ? INFINITY : -INFINITY;
+        lo0 = h0 ? lo0 : 0.0f; lo1 = h1 ? lo1 : 0.0f;
     }
-    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-    bool both = h0 && h1, none = !h0 && !h1;
-    bool take1 = h1 && (!h0 || e1 < e0);            // descend into child 1
-    int near_c = take1 ? c1 : c0, far_c = take1 ? c0 : c1;
-    if (both) *top = far_c;
-    top += both ? stride : 0;
-    top -= none ? stride : 0;
-    if (none) near_c = *top;
-    node = near_c;
+    // Three outcomes, no branch: both children hit -> push the farther, descend into the nearer;
+    // one hit -> descend into it; none -> pop.  Written as PTX so the predicates stay predicates
+    // (the C++ forms were compiled to select/LOP3/ISETP chains: 17-19 instructions against 13).
+    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y), next;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred h0, h1, sw, t1, both, none;\n\t"
+        ".reg .b32 far;\n\t"
+        "setp.le.f32 h0, %2, %3;\n\t"
+        "setp.le.f32 h1, %4, %5;\n\t"
+        "setp.lt.f32 sw, %4, %2;\n\t"
+        "and.pred both, h0, h1;\n\t"
+        "or.pred none, h0, h1;\n\t"
+        "not.pred none, none;\n\t"
+        "not.pred t1, h0;\n\t"
+        "or.pred t1, t1, sw;\n\t"
+        "and.pred t1, t1, h1;\n\t"
+        "selp.b32 %0, %7, %6, t1;\n\t"
+        "selp.b32 far, %6, %7, t1;\n\t"
+        "@both st.shared.b32 [%1], far;\n\t"
+        "@both add.u32 %1, %1, %8;\n\t"
+        "@none sub.u32 %1, %1, %8;\n\t"
+        "@none ld.shared.b32 %0, [%1];\n\t"
+        "}"
+        : "=&r"(next), "+r"(top)
+        : "f"(lo0), "f"(hi0), "f"(lo1), "f"(hi1), "r"(c0), "r"(c1), "r"(stride_bytes)
+        : "memory");
+    node = next;
 }
 
 template <bool COUNT, class Acc>
-__device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, int*& top, int stride, float t_min, Closest& c,
+__device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, uint32_t& top, int stride_bytes, float t_min, Closest& c,
                                             int& node, TravCounters& tc) {
     if (COUNT) tc.prims++;
     hit_leaf(r, acc, node, t_min, c);
-    top -= stride; node = *top;
+    top -= stride_bytes;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(node) : "r"(top) : "memory");
 }
 
 template <bool COUNT, class Acc>
