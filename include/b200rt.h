@@ -148,7 +148,9 @@ typedef struct B200rtCamera {
 
 /* ---- render parameters: RenderSettings (src/argparse.rs:107-123) + sharding ------------- */
 #define B200RT_FLAG_COUNT_TRAVERSAL 1u  /* also count BVH node visits / primitive tests (slower) */
-#define B200RT_FLAG_ACCUMULATE      2u  /* device API: add to the buffer instead of overwriting */
+#define B200RT_FLAG_ACCUMULATE      2u  /* add to the buffer instead of overwriting (progressive rendering): device API, and
+                                           the host API when `accum` is given — its contents are uploaded first and
+                                           the RGB8 output is resolved with n = the summed sample count (.w)          */
 
 typedef struct B200rtRenderParams {
     uint32_t samples;           /* per pixel, this call; 0 is coerced to 1 (src/main.rs:75-80) */

@@ -56,6 +56,16 @@ int  b200rt_host_camera(const double look_from[3], const double look_at[3], cons
 int  b200rt_host_default_camera(uint32_t width, double vfov_degrees, double focal_length, double aperture,
                                 uint32_t ratio_num, uint32_t ratio_den, B200rtCamera* out);
 
+/* Accumulation-buffer checkpoint for long progressive runs (BASELINE config 5: 4096 spp): the W*H float4
+ * {sum r, g, b, n} buffer of b200rt_render plus what is needed to continue the SAME sample sequence —
+ * the seed and the number of samples done (the next call's sample_offset).  Little-endian file:
+ * "B200RTAC", u32 version, u32 W, u32 H, u32 samples_done, u64 seed, W*H*4 f32, u32 CRC-32 of the floats.
+ * _load allocates *accum (release with b200rt_free) and fails on a bad magic, size or CRC. */
+int  b200rt_host_checkpoint_save(const char* path, const float* accum, uint32_t width, uint32_t height,
+                                 uint32_t samples_done, uint64_t seed);
+int  b200rt_host_checkpoint_load(const char* path, uint32_t* width, uint32_t* height, uint32_t* samples_done,
+                                 uint64_t* seed, float** accum);
+
 /* render_scene (src/main.rs:65-130) end to end: upload, render, resolve, write the PNG.
  * output_png may be NULL (no file).  rgb8_out may be NULL, else W*H*3 bytes, top row first. */
 int  b200rt_host_render_scene(const B200rtHostScene* scene, const B200rtCamera* camera,

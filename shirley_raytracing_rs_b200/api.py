@@ -270,6 +270,25 @@ def decode_jpeg(data: bytes) -> np.ndarray:
         lib.b200rt_free(out)
 
 
+def checkpoint_save(path: str, accum: np.ndarray, samples_done: int, seed: int) -> None:
+    """Write an accumulation-buffer checkpoint ((H, W, 4) float32 sums + the state to continue the sample sequence)."""
+    accum = np.ascontiguousarray(accum, dtype=np.float32)
+    h, w, c = accum.shape
+    assert c == 4
+    F.check(lib.b200rt_host_checkpoint_save(str(path).encode(), accum.ctypes.data, w, h, samples_done, seed), host=True)
+
+
+def checkpoint_load(path: str):
+    """-> (accum (H, W, 4) float32, samples_done, seed)"""
+    w, h, n, seed, out = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_void_p()
+    F.check(lib.b200rt_host_checkpoint_load(str(path).encode(), C.byref(w), C.byref(h), C.byref(n), C.byref(seed), C.byref(out)), host=True)
+    try:
+        acc = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_float)), shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib.b200rt_free(out)
+    return acc, n.value, seed.value
+
+
 # ---- camera (camera/mod.rs) -------------------------------------------------------------------------
 def camera(look_from, look_at, up=(0.0, 1.0, 0.0), *, vfov=20.0, focal_length=1.0, aperture: Optional[float] = 0.001,
            width: int = 0, height: int = 0, aspect_ratio=(3, 2), focus_length: float = 0.0) -> F.Camera:
@@ -293,13 +312,20 @@ def default_camera(width=640, camera_fov=20.0, camera_focal_length=1.0, camera_a
 
 # ---- render (src/main.rs:65-130, render.rs) ------------------------------------------------------------
 def render(scene: Scene, cam: F.Camera, samples: int = 100, max_depth: int = 50, seed: int = 0, *, sample_offset: int = 0,
-           rows=(0, 0), shard=(1, 0), count_traversal: bool = False, device: int = -1):
+           rows=(0, 0), shard=(1, 0), count_traversal: bool = False, device: int = -1, into: Optional[np.ndarray] = None):
     """The frame loop of render_scene: returns (accum[H, W, 4] float32 {sum r,g,b, n}, Stats).
-    Row 0 is the bottom of the picture (image.rs:36-38)."""
+    Row 0 is the bottom of the picture (image.rs:36-38).  `into` = an earlier result (or a checkpoint):
+    the new samples are ADDED to it (progressive rendering; give sample_offset = samples already done)."""
     H, W = cam.image_height, cam.image_width
-    accum = np.empty((H, W, 4), dtype=np.float32)
+    flags = F.FLAG_COUNT_TRAVERSAL if count_traversal else 0
+    if into is not None:
+        if into.shape != (H, W, 4) or into.dtype != np.float32 or not into.flags.c_contiguous:
+            raise ValueError("`into` must be a C-contiguous float32 array of shape (H, W, 4)")
+        accum, flags = into, flags | F.FLAG_ACCUMULATE
+    else:
+        accum = np.empty((H, W, 4), dtype=np.float32)
     p = F.RenderParams(samples=samples, sample_offset=sample_offset, max_depth=max_depth,
-                       flags=F.FLAG_COUNT_TRAVERSAL if count_traversal else 0, seed=seed, row_begin=rows[0], row_end=rows[1],
+                       flags=flags, seed=seed, row_begin=rows[0], row_end=rows[1],
                        shard_count=shard[0], shard_index=shard[1], device=-1)
     st = F.Stats()
     F.check(lib.b200rt_render(scene.device(device), C.byref(cam), C.byref(p), accum.ctypes.data, C.byref(st)))

@@ -32,6 +32,7 @@ struct Args {
     bool night = false;
     std::string scene_output;
     uint64_t seed = 0x5EED5EEDull;
+    std::string checkpoint;     // extra: accumulation-buffer checkpoint (resumed if it exists)
 };
 
 [[noreturn]] void usage(const char* msg) {
@@ -51,7 +52,9 @@ struct Args {
             "      --camera-aspect-ratio <R>    std3x2|std16x9|std16x10|square|target-iphone [default: std3x2]\n"
             "      --night                      (random) Render at night time!\n"
             "      --scene-output <FILE>        (random) Output file for scene_data\n"
-            "      --seed <N>                   seed for scene generation and sampling\n");
+            "      --seed <N>                   seed for scene generation and sampling\n"
+            "      --checkpoint <FILE>          save the accumulation buffer there; if FILE exists, continue from it:\n"
+            "                                   --samples more samples are added (same scene, camera and seed required)\n");
     exit(msg ? 2 : 0);
 }
 
@@ -86,6 +89,7 @@ Args parse(int argc, char** argv) {
         else if (s == "--night") a.night = true;
         else if (s == "--scene-output") a.scene_output = need("--scene-output");
         else if (s == "--seed") a.seed = strtoull(need("--seed").c_str(), nullptr, 0);
+        else if (s == "--checkpoint") a.checkpoint = need("--checkpoint");
         else if (!s.empty() && s[0] == '-') usage(("unexpected argument " + s).c_str());
         else pos.push_back(s);
     }
@@ -110,7 +114,29 @@ int render_scene(const Args& args, const scene::SceneBuilder& builder, const cam
     B200rtRenderParams p{};
     p.samples = (uint32_t)samples; p.max_depth = (uint32_t)args.max_reflect; p.seed = args.seed; p.device = -1;
     B200rtStats st{};
-    rc = b200rt_render_rgb8(dev, &c, &p, rgb.data(), nullptr, &st);
+    if (args.checkpoint.empty()) {
+        rc = b200rt_render_rgb8(dev, &c, &p, rgb.data(), nullptr, &st);
+    } else {
+        // progressive: continue the checkpoint's sample sequence (same seed, sample_offset = samples done)
+        const size_t n = (size_t)c.image_width * c.image_height * 4;
+        std::vector<float> accum(n, 0.0f);
+        uint32_t cw = 0, ch = 0, done = 0; uint64_t cseed = 0; float* loaded = nullptr;
+        if (std::ifstream(args.checkpoint).good()) {
+            rc = b200rt_host_checkpoint_load(args.checkpoint.c_str(), &cw, &ch, &done, &cseed, &loaded);
+            if (rc) { b200rt_scene_destroy(dev); fprintf(stderr, " ERROR %s\n", b200rt_host_last_error()); return rc; }
+            bool same = cw == c.image_width && ch == c.image_height && cseed == args.seed;
+            if (same) memcpy(accum.data(), loaded, n * sizeof(float));
+            b200rt_free(loaded);
+            if (!same) { b200rt_scene_destroy(dev); fprintf(stderr, " ERROR checkpoint %s was written for another image size or seed\n", args.checkpoint.c_str()); return B200RT_EINVAL; }
+            if (args.verbose >= 1) fprintf(stderr, " INFO  resuming %s: %u samples done\n", args.checkpoint.c_str(), done);
+        }
+        p.sample_offset = done; p.flags |= B200RT_FLAG_ACCUMULATE;
+        rc = b200rt_render_rgb8(dev, &c, &p, rgb.data(), accum.data(), &st);
+        if (!rc) {
+            rc = b200rt_host_checkpoint_save(args.checkpoint.c_str(), accum.data(), c.image_width, c.image_height, done + (uint32_t)samples, args.seed);
+            if (rc) fprintf(stderr, " ERROR %s\n", b200rt_host_last_error());
+        }
+    }
     b200rt_scene_destroy(dev);
     if (rc) { fprintf(stderr, " ERROR %s\n", b200rt_last_error()); return rc; }
     if (args.verbose >= 1)

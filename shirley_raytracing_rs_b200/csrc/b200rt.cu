@@ -1620,12 +1620,21 @@ static int render_host_impl(const B200rtScene* csc, const B200rtCamera* cam, con
         if (e != cudaSuccess) return done(fail(B200RT_ENOMEM, "rgb8 buffer: %s", cudaGetErrorString(e)));
         scr->rgb_bytes = px * 3;
     }
-    B200rtRenderParams p = *prm; p.flags &= ~B200RT_FLAG_ACCUMULATE;
+    // Progressive rendering with host buffers: with B200RT_FLAG_ACCUMULATE the caller's float4 sums
+    // (an earlier call's output, or a checkpoint) are uploaded first and the new samples are added.
+    B200rtRenderParams p = *prm;
+    const bool progressive = (p.flags & B200RT_FLAG_ACCUMULATE) && accum;
+    if (!progressive) p.flags &= ~B200RT_FLAG_ACCUMULATE;
+    if (progressive) {
+        cudaError_t eu = cudaMemcpyAsync(scr->d_accum, accum, px * sizeof(float4), cudaMemcpyHostToDevice, scr->own_stream);
+        if (eu != cudaSuccess) return done(fail(B200RT_ECUDA, "H2D copy of the accumulation buffer: %s", cudaGetErrorString(eu)));
+    }
     rc = launch_render(sc, cam, &p, reinterpret_cast<float*>(scr->d_accum), scr->own_stream, scr);
     if (rc) return done(rc);
     cudaError_t e = cudaSuccess;
     if (out_rgb8) {
-        rc = b200rt_resolve_rgb8_device(reinterpret_cast<float*>(scr->d_accum), cam->image_width, cam->image_height, p.samples == 0 ? 1 : p.samples, scr->d_rgb, scr->own_stream);
+        // progressive: n = the summed sample count in .w
+        rc = b200rt_resolve_rgb8_device(reinterpret_cast<float*>(scr->d_accum), cam->image_width, cam->image_height, progressive ? 0 : (p.samples == 0 ? 1 : p.samples), scr->d_rgb, scr->own_stream);
         if (rc) return done(rc);
         scr->launches += 1;
         e = cudaMemcpyAsync(out_rgb8, scr->d_rgb, px * 3, cudaMemcpyDeviceToHost, scr->own_stream);

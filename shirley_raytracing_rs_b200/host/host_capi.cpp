@@ -1,4 +1,7 @@
 // host_capi.cpp — C shim of include/b200rt_host.h over raytracer.hpp.
+#include <zlib.h>
+
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -93,6 +96,40 @@ int b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, u
         *width = img.width; *height = img.height; *rgb8 = buf;
         return B200RT_OK;
     } catch (const std::exception& e) { return host_fail(B200RT_EINVAL, e.what()); }
+}
+
+int b200rt_host_checkpoint_save(const char* path, const float* accum, uint32_t W, uint32_t H, uint32_t samples_done, uint64_t seed) {
+    if (!path || !accum || W == 0 || H == 0) return host_fail(B200RT_EINVAL, "bad argument");
+    std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return host_fail(B200RT_EIO, "cannot create " + tmp);
+    const size_t n = (size_t)W * H * 4;
+    uint32_t hdr[4] = {1u, W, H, samples_done};
+    uint32_t crc = (uint32_t)crc32_z(0L, reinterpret_cast<const unsigned char*>(accum), n * sizeof(float));
+    bool ok = fwrite("B200RTAC", 1, 8, f) == 8 && fwrite(hdr, 4, 4, f) == 4 && fwrite(&seed, 8, 1, f) == 1 &&
+              fwrite(accum, sizeof(float), n, f) == n && fwrite(&crc, 4, 1, f) == 1;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return host_fail(B200RT_EIO, std::string("cannot write ") + path); }   // atomic replace
+    return B200RT_OK;
+}
+
+int b200rt_host_checkpoint_load(const char* path, uint32_t* W, uint32_t* H, uint32_t* samples_done, uint64_t* seed, float** accum) {
+    if (!path || !W || !H || !samples_done || !seed || !accum) return host_fail(B200RT_EINVAL, "NULL argument");
+    *accum = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return host_fail(B200RT_EIO, std::string("cannot open ") + path);
+    char magic[8]; uint32_t hdr[4]; uint64_t sd = 0;
+    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, "B200RTAC", 8) == 0 && fread(hdr, 4, 4, f) == 4 && fread(&sd, 8, 1, f) == 1;
+    if (!ok || hdr[0] != 1u || hdr[1] == 0 || hdr[2] == 0 || (uint64_t)hdr[1] * hdr[2] > 0xFFFFFFFFull) { fclose(f); return host_fail(B200RT_EINVAL, std::string(path) + " is not a b200rt checkpoint (version 1)"); }
+    const size_t n = (size_t)hdr[1] * hdr[2] * 4;
+    float* buf = (float*)malloc(n * sizeof(float));
+    if (!buf) { fclose(f); return host_fail(B200RT_ENOMEM, "out of memory"); }
+    uint32_t crc = 0;
+    ok = fread(buf, sizeof(float), n, f) == n && fread(&crc, 4, 1, f) == 1;
+    fclose(f);
+    if (!ok || crc != (uint32_t)crc32_z(0L, reinterpret_cast<const unsigned char*>(buf), n * sizeof(float))) { free(buf); return host_fail(B200RT_EIO, std::string(path) + ": truncated or corrupt checkpoint (CRC mismatch)"); }
+    *W = hdr[1]; *H = hdr[2]; *samples_done = hdr[3]; *seed = sd; *accum = buf;
+    return B200RT_OK;
 }
 
 int b200rt_host_camera(const double from[3], const double at[3], const double up[3], double vfov, double focal_length, double aperture,

@@ -66,3 +66,21 @@ def test_render_end_to_end(tmp_path, gpu_required):
     assert Image.open(tmp_path / "c.png").size == (64, 64)
     r = run("render", "earth", "--camera-aspect-ratio", "std16x9", "-w", "160", "-s", "2", "-o", "/nonexistent-dir/x.png")
     assert r.returncode == 1 and "cannot write" in r.stderr
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_equals_one_run(tmp_path, gpu_required):
+    """--checkpoint: 3 + 5 samples in two invocations == 8 samples in one (same sample sequence,
+    fixed-point tile sums: identical RGB bytes)."""
+    from PIL import Image
+    ck = tmp_path / "acc.ckpt"
+    a, b, full = tmp_path / "a.png", tmp_path / "b.png", tmp_path / "full.png"
+    common = ("render", "random", "--seed", "11", "-w", "120")
+    r = run(*common, "-s", "3", "-o", str(a), "--checkpoint", str(ck)); assert r.returncode == 0, r.stderr
+    r = run("-v", *common, "-s", "5", "-o", str(b), "--checkpoint", str(ck)); assert r.returncode == 0, r.stderr
+    assert "resuming" in r.stderr and "3 samples done" in r.stderr
+    r = run(*common, "-s", "8", "-o", str(full)); assert r.returncode == 0, r.stderr
+    got, want = np.asarray(Image.open(b).convert("RGB")).astype(int), np.asarray(Image.open(full).convert("RGB")).astype(int)
+    assert np.abs(got - want).max() <= 1 and (got != want).mean() < 1e-3          # f32 sum of two launches vs one: last-bit differences only
+    r = run(*common, "-s", "1", "-w", "90", "-o", str(a), "--checkpoint", str(ck))   # other image size: refused
+    assert r.returncode == 1 and "another image size or seed" in r.stderr

@@ -388,3 +388,18 @@ def test_resolve_peers_equals_sum_then_resolve(rt, gpu_required):
         assert np.array_equal(out.cpu().numpy(), want)
     with pytest.raises(rt.B200rtError):
         F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, 17, W, H, 60, 0, 0, out.data_ptr(), None))
+
+
+def test_progressive_accumulation_matches_one_launch(rt, weekend, gpu_required):
+    """B200RT_FLAG_ACCUMULATE through the host API: samples [0,4) then [4,10) added into the same buffer ==
+    10 samples at once (streams are keyed by (pixel, sample index)); .w counts the samples."""
+    cam = rt.default_camera(160)
+    full, st_full = rt.render(weekend, cam, samples=10, seed=21)
+    acc, st_a = rt.render(weekend, cam, samples=4, seed=21)
+    acc2, st_b = rt.render(weekend, cam, samples=6, seed=21, sample_offset=4, into=acc)
+    assert acc2 is acc and np.all(acc[..., 3] == 10.0)
+    assert st_a.rays + st_b.rays == st_full.rays
+    np.testing.assert_allclose(acc[..., :3], full[..., :3], rtol=3e-6, atol=1e-6)
+    rgb_p = rt.resolve_rgb8(acc)                     # samples=0: n from .w
+    rgb_f = rt.resolve_rgb8(full, samples=10)
+    assert np.abs(rgb_p.astype(int) - rgb_f.astype(int)).max() <= 1

@@ -104,3 +104,26 @@ def test_other_factories(rt):
     assert 1500 < scaled.n_prims < 1610
     lat = rt.Scene.named("lattice", param=2).desc.contents
     assert lat.n_prims == 64
+
+
+def test_checkpoint_roundtrip_and_corruption(rt, tmp_path):
+    """Accumulation-buffer checkpoint (include/b200rt_host.h): exact round trip; bad files are refused."""
+    rng = np.random.default_rng(4)
+    acc = rng.uniform(0, 500, size=(19, 23, 4)).astype(np.float32)
+    path = tmp_path / "frame.ckpt"
+    rt.checkpoint_save(path, acc, samples_done=137, seed=0xDEADBEEF12345678)
+    got, done, seed = rt.checkpoint_load(path)
+    assert np.array_equal(got, acc) and done == 137 and seed == 0xDEADBEEF12345678
+    raw = bytearray(path.read_bytes())
+    raw[200] ^= 0x40                                        # flip one bit of the payload
+    (tmp_path / "bad.ckpt").write_bytes(bytes(raw))
+    with pytest.raises(rt.B200rtError, match="CRC"):
+        rt.checkpoint_load(tmp_path / "bad.ckpt")
+    (tmp_path / "short.ckpt").write_bytes(bytes(raw[:100]))
+    with pytest.raises(rt.B200rtError):
+        rt.checkpoint_load(tmp_path / "short.ckpt")
+    (tmp_path / "junk.ckpt").write_bytes(b"PNG\x00" * 64)
+    with pytest.raises(rt.B200rtError, match="not a b200rt checkpoint"):
+        rt.checkpoint_load(tmp_path / "junk.ckpt")
+    with pytest.raises(rt.B200rtError):
+        rt.checkpoint_load(tmp_path / "missing.ckpt")
