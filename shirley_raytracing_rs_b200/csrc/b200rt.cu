@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
     // per-warp queue of generated primary rays, SoA [RAYQ_FIELDS][RAYQ_SLOTS] behind the accumulators
     uint32_t* rayq = reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
                      + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
-    const TopPrims top = top_of(a.scene);
     const float T_MIN = 0.001f;                      // render.rs:31
     const bool has_perlin = a.scene.perlin != nullptr;
 
@@ -303,7 +302,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         for (int k = lane; k < 96; k += 32) wacc[k] = 0;
         __syncwarp();
         uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
-        uint32_t nrays = 0, nexh = 0, npaths = 0;
+        uint32_t nrays = 0, nexh = 0;   // nrays: warp total (same value in every lane), nexh: per lane
         TravCounters tc; tc.nodes = 0; tc.prims = 0;
         bool alive = false;
         Rng rng; rng.state = 0; rng.inc = 1;
@@ -393,7 +392,6 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 depth = a.max_depth;
                 alive = depth > 0;
                 setup = alive;
-                ++npaths;
             }
             {
                 uint32_t taken = min(want, q_count);
@@ -411,9 +409,16 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
                 ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
                 c.t = INFINITY; c.code = -1; c.face = 0;
-                hit_top_prims<COUNT>(ray, acc, top, T_MIN, c, tc, &inv_e);
-                node = 0; top_sp = stack_s + BLK * 4; ++nrays;
+                // the list is indexed in the kernel parameters (constant bank): a register copy indexed by a
+                // loop counter would live in local memory
+#pragma unroll 1
+                for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
+                    if (COUNT) tc.prims++;
+                    hit_leaf(ray, acc, a.scene.top_prims[k], T_MIN, c, &inv_e);
+                }
+                node = 0; top_sp = stack_s + BLK * 4;
             }
+            nrays += (uint32_t)__popc(__ballot_sync(FULL, setup));   // warp-uniform count: no per-lane counter to keep live
 
             // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
             for (;;) {
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             *dst = v;
         }
         __syncwarp();
-        w_rays += nrays; w_exh += nexh; w_paths += npaths;
+        w_rays += lane == 0 ? nrays : 0u; w_exh += nexh; w_paths += lane == 0 ? n_items : 0u;   // every work-list item became one path
         if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
     }
     for (int o = 16; o > 0; o >>= 1) {
