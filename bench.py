@@ -331,7 +331,7 @@ def main():
                     "frac": achieved / fp32_peak if fp32_peak else None,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
                     # profiles/r01_ncu_metrics.md): the scene is staged in shared memory, HBM is idle
-                    "traffic": 543744, "traffic_unit": "bytes per launch (ncu capture of a 50-spp launch)",
+                    "traffic": 2018560, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one 50-spp launch (ncu --set full, profiles/r01_ncu_metrics.md); the 15 MB accumulation buffer is written once and stays in L2",
                     "kernel": "path_trace_kernel_v2", "kernel_ms": float(np.mean(kernel_ms)),
                     "ops_per_ray": ops_per_ray, "node_visits_per_ray": cst.node_visits / cst.rays, "prim_tests_per_ray": cst.prim_tests / cst.rays,
                     "segments_per_sample": cst.rays / cst.paths,
