@@ -182,6 +182,8 @@ typedef struct B200rtStats {
 typedef struct B200rtSceneInfo {
     uint32_t n_prims, n_bvh_nodes, bvh_depth, bvh_nodes_in_smem;
     uint64_t device_bytes;
+    float    bvh_build_ms;      /* tree construction alone (host wall time, or device time for the device builder) */
+    uint32_t bvh_builder;       /* 0 = binned SAH on the host, 1 = linear BVH built on the device (large scenes) */
 } B200rtSceneInfo;
 
 typedef struct B200rtScene B200rtScene;    /* opaque, immutable after create */

@@ -13,6 +13,7 @@ _, sc = rt.render(s, cam, samples=spp, seed=2, count_traversal=True)
 info = s.info()
 nv, pt = sc.node_visits / sc.rays, sc.prim_tests / sc.rays
 bytes_per_ray = 64 * nv + 16 * pt + 32
-print(f"C4 G={G}: objects {info.n_prims} nodes {info.n_bvh_nodes} depth {info.bvh_depth} top nodes in smem {info.bvh_nodes_in_smem} device MB {info.device_bytes / 1e6:.1f}")
+print(f"C4 G={G}: objects {info.n_prims} nodes {info.n_bvh_nodes} depth {info.bvh_depth} top nodes in smem {info.bvh_nodes_in_smem} device MB {info.device_bytes / 1e6:.1f}  "
+      f"builder {'device LBVH' if info.bvh_builder else 'host SAH'} {info.bvh_build_ms:.1f} ms")
 print(f"  {spp} spp: kernel {st.kernel_ms:.1f} ms  {st.rays / st.kernel_ms / 1e3:.0f} Mrays/s  node visits/ray {nv:.2f}  prim tests/ray {pt:.2f}  "
       f"algorithmic bytes/ray {bytes_per_ray:.0f} -> {st.rays / st.kernel_ms / 1e6 * bytes_per_ray:.0f} GB/s")

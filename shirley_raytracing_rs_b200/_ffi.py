@@ -94,7 +94,7 @@ class Stats(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [("n_prims", C.c_uint32), ("n_bvh_nodes", C.c_uint32), ("bvh_depth", C.c_uint32),
-                ("bvh_nodes_in_smem", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("bvh_nodes_in_smem", C.c_uint32), ("device_bytes", C.c_uint64), ("bvh_build_ms", C.c_float), ("bvh_builder", C.c_uint32)]
 
 
 class Ray(C.Structure):

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -22,6 +23,7 @@
 #include <vector>
 
 #include "bvh_build.hpp"
+#include "lbvh.cuh"
 #include "rt_device.cuh"
 
 namespace b200rt {
@@ -47,6 +49,7 @@ static int fail(int code, const char* fmt, ...) {
 // kernel arguments
 // ------------------------------------------------------------------------------------------
 constexpr int BLOCK = 256;          // threads per CTA (8 warps)
+constexpr size_t LBVH_AUTO_MIN = 262144;   // primitives from which scene_create builds the tree on the device
 constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
 
 struct SmemPlan {
@@ -1278,6 +1281,16 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
                    : (kernel_version == 2 ? (size_t)(block_threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)) : 0);
     SmemPlan plan = make_plan(sc, target_blocks, block_threads, extra);
     if (!plan.all_in_smem && target_blocks > 1) { SmemPlan p1 = make_plan(sc, 1, block_threads, extra); if (p1.all_in_smem) plan = p1; }
+#ifndef B200RT_DEV_BUILD
+    // A deep tree (the device-built linear BVH can reach 40-50 levels) needs more stack per thread than
+    // 768 threads leave room for: fall back to smaller CTAs rather than fail.
+    while (kernel_version == 2 && plan.bytes + 1024 > sc->smem_optin && block_threads > 256) {
+        block_threads = block_threads > 512 ? 512 : 256;
+        target_blocks = 1;
+        extra = (size_t)(block_threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t));
+        plan = make_plan(sc, target_blocks, block_threads, extra);
+    }
+#endif
     a.plan = plan;
 
     scr->launches = 0;
@@ -1465,8 +1478,24 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     // within ~8x the scene extent (checked per launch).  A box only culls.
     float pad = max_abs * 4e-6f;
     for (auto& bp : bprims) for (int k = 0; k < 3; ++k) { bp.box.lo[k] -= pad; bp.box.hi[k] += pad; }
-    BvhBuildResult bvh = build_bvh(std::move(bprims));
-    if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
+    // Builder: binned SAH on the host (bvh_build.hpp), or — for scenes large enough that the host build
+    // would dominate a frame — the linear BVH built on the device (lbvh.cuh).  B200RT_BUILDER=sah|lbvh forces one.
+    bool use_lbvh = bprims.size() >= LBVH_AUTO_MIN;
+    if (const char* v = getenv("B200RT_BUILDER")) { if (!strcmp(v, "lbvh")) use_lbvh = true; else if (!strcmp(v, "sah")) use_lbvh = false; }
+    if (bprims.size() < 2) use_lbvh = false;
+    HostBox lbvh_bounds; detail::box_init(lbvh_bounds);
+    std::vector<BuildPrim> lbvh_prims;
+    BvhBuildResult bvh;
+    float host_build_ms = 0.f;
+    if (use_lbvh) {
+        for (auto& bp : bprims) detail::box_grow(lbvh_bounds, bp.box);
+        lbvh_prims.swap(bprims);
+    } else {
+        auto t0 = std::chrono::steady_clock::now();
+        bvh = build_bvh(std::move(bprims));
+        host_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
+    }
 
     std::vector<TexRec> tex(d->n_textures);
     for (uint32_t t = 0; t < d->n_textures; ++t) {
@@ -1493,6 +1522,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     // half-extent (rt_device.cuh: aabb_center).  The box is re-derived outwards: c = (lo+hi)/2,
     // h = max(hi - c, c - lo) bumped up one ulp, so [c - h, c + h] contains [lo, hi].  An empty
     // child (lo > hi) gets h = -1: near > far on every axis, never entered.
+    const size_t n_nodes = use_lbvh ? lbvh_prims.size() - 1 : nodes.size();
     std::vector<BvhNode> cnodes(nodes.size());
     for (size_t i = 0; i < nodes.size(); ++i) {
         const float* q = reinterpret_cast<const float*>(&nodes[i]);
@@ -1512,8 +1542,9 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         o[12] = q[12]; o[13] = q[13]; o[14] = q[14]; o[15] = q[15];
     }
     Arena arena;
-    size_t off_nodes = arena.put(nodes), off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
-    size_t off_cnodes = arena.put(cnodes);
+    size_t off_nodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(nodes);
+    size_t off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
+    size_t off_cnodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(cnodes);
     // images: RGB8 -> RGBA8 so a texel is one 4-byte load
     std::vector<ImageRec> images(d->n_images);
     std::vector<size_t> off_img(d->n_images);
@@ -1545,6 +1576,14 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     }
     sc->ds.nodes = reinterpret_cast<const BvhNode*>(dbase + off_nodes);
     sc->ds.cnodes = reinterpret_cast<const BvhNode*>(dbase + off_cnodes);
+    if (use_lbvh) {
+        uint32_t depth = 0; float ms = 0.f;
+        cudaError_t e = lbvh::build(lbvh_prims, lbvh_bounds, reinterpret_cast<BvhNode*>(dbase + off_nodes), reinterpret_cast<BvhNode*>(dbase + off_cnodes), &depth, &ms);
+        if (e != cudaSuccess) return bail(fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, "device BVH build: %s", cudaGetErrorString(e)));
+        if (depth > 60) return bail(fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack (B200RT_BUILDER=sah builds a shallower tree)", depth));
+        bvh.depth = depth;
+        sc->info.bvh_build_ms = ms; sc->info.bvh_builder = 1;
+    } else { sc->info.bvh_build_ms = host_build_ms; sc->info.bvh_builder = 0; }
     sc->ds.geom = reinterpret_cast<const GeomRec*>(dbase + off_geom);
     sc->ds.mats = reinterpret_cast<const MatRec*>(dbase + off_mats);
     sc->ds.tex = reinterpret_cast<const TexRec*>(dbase + off_tex);
@@ -1553,7 +1592,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     sc->ds.n_top_prims = ds_top.n_top_prims;
     for (int k = 0; k < 7; ++k) sc->ds.top_prims[k] = ds_top.top_prims[k];
     sc->box_pad = pad; sc->max_abs_coord = max_abs;
-    sc->ds.n_nodes = (uint32_t)nodes.size(); sc->ds.n_prims = d->n_prims; sc->ds.n_tex = d->n_textures; sc->ds.bvh_depth = bvh.depth;
+    sc->ds.n_nodes = (uint32_t)n_nodes; sc->ds.n_prims = d->n_prims; sc->ds.n_tex = d->n_textures; sc->ds.bvh_depth = bvh.depth;
     sc->ds.sky_kind = d->skybox.kind == B200RT_SKY_ABOVE ? B200RT_SKY_ABOVE : B200RT_SKY_FLAT;
     bool flat = d->skybox.kind == B200RT_SKY_FLAT;
     sc->ds.sky_r = flat ? d->skybox.rgb[0] : 0.f; sc->ds.sky_g = flat ? d->skybox.rgb[1] : 0.f; sc->ds.sky_b = flat ? d->skybox.rgb[2] : 0.f;

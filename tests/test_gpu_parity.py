@@ -403,3 +403,31 @@ def test_progressive_accumulation_matches_one_launch(rt, weekend, gpu_required):
     rgb_p = rt.resolve_rgb8(acc)                     # samples=0: n from .w
     rgb_f = rt.resolve_rgb8(full, samples=10)
     assert np.abs(rgb_p.astype(int) - rgb_f.astype(int)).max() <= 1
+
+
+# ---- K5: the BVH built on the device (linear BVH, lbvh.cuh) --------------------------------------------------
+@pytest.mark.parametrize("name,param,scale", [("scaled", 40, 45.0), ("lattice", 4, 6.0), ("random", 0, 8.0), ("cornell", 0, 500.0)])
+def test_device_built_bvh_gives_the_same_hits(rt, po, gpu_required, monkeypatch, name, param, scale):
+    """Closest-hit results do not depend on the tree: with B200RT_BUILDER=lbvh ids, t and normals stay
+    bit-identical to the f32 mirror (and to the host-built SAH tree), and renders are bit-identical too."""
+    rays = random_rays(150_000, 9, origin_scale=scale)
+    if name == "cornell":
+        rays[:, :3] = np.abs(rays[:, :3]) % 555.0
+    monkeypatch.setenv("B200RT_BUILDER", "lbvh")
+    s = rt.Scene.named(name, seed=11, param=param)
+    ids, hits, _ = rt.closest_hit(s, rays, 0.001, INF)
+    info = s.info()
+    assert info.bvh_builder == 1 and info.n_bvh_nodes >= 1 and info.bvh_depth >= 1
+    want = po.closest_hit_gpu32(s.desc, rays, 0.001, INF)
+    assert np.array_equal(ids, want["id"])
+    hit = ids >= 0
+    assert np.array_equal(hits["t"][hit], want["t"][hit]) and np.array_equal(hits["n"][hit], want["n"][hit])
+    cam = rt.default_camera(96) if name != "cornell" else rt.camera((278, 278, -800), (278, 278, 0), vfov=40, aperture=None, width=64, aspect_ratio=(1, 1), focus_length=10.0)
+    img_l, st_l = rt.render(s, cam, samples=4, seed=3)
+    monkeypatch.setenv("B200RT_BUILDER", "sah")
+    s2 = rt.Scene.named(name, seed=11, param=param)
+    assert s2.info().bvh_builder == 0
+    ids2, _, _ = rt.closest_hit(s2, rays, 0.001, INF)
+    assert np.array_equal(ids, ids2)
+    img_s, st_s = rt.render(s2, cam, samples=4, seed=3)
+    assert np.array_equal(img_l, img_s) and st_l.rays == st_s.rays
