@@ -1103,10 +1103,20 @@ int resolve_device(int device, int* out) {
 // Scene arrays are packed into ONE pinned staging buffer and uploaded with ONE copy into ONE
 // device arena (256-byte aligned sub-allocations): a frame that re-creates its scene pays one
 // cudaMalloc + one H2D copy.
+// Layout of the one device allocation that holds every scene array.  Only offsets are assigned here;
+// each array is copied straight from where it lies on the host (a host-side staging copy of a
+// 1e6-sphere scene — 208 MB, grown piecewise — took 230 ms of scene_create's 360).
 struct Arena {
-    std::vector<uint8_t> host;
-    size_t reserve(size_t bytes) { size_t off = (host.size() + 255) & ~size_t(255); host.resize(off + std::max<size_t>(bytes, 16)); return off; }
-    template <class T> size_t put(const std::vector<T>& v) { size_t off = reserve(v.size() * sizeof(T)); if (!v.empty()) memcpy(host.data() + off, v.data(), v.size() * sizeof(T)); return off; }
+    struct Seg { const void* src; size_t bytes, off; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    size_t reserve(size_t bytes) { size_t off = (total + 255) & ~size_t(255); total = off + std::max<size_t>(bytes, 16); return off; }
+    size_t put(const void* src, size_t bytes) { size_t off = reserve(bytes); if (bytes) segs.push_back({src, bytes, off}); return off; }
+    template <class T> size_t put(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }   // v must outlive upload()
+    cudaError_t upload(uint8_t* dbase) const {
+        for (const Seg& g : segs) { cudaError_t e = cudaMemcpy(dbase + g.off, g.src, g.bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return e; }
+        return cudaSuccess;
+    }
 };
 
 int validate(const B200rtSceneDesc* d) {
@@ -1403,7 +1413,17 @@ int b200rt_device_count(void) {
 int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out) {
     if (!out) return fail(B200RT_EINVAL, "out is NULL");
     *out = nullptr;
+    // B200RT_TIMING=1: wall time of each phase on stderr (large scenes: where scene_create's time goes)
+    const bool timing = getenv("B200RT_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[b200rt] scene_create %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     int rc = validate(d); if (rc) return rc;
+    lap("validate");
     rc = resolve_device(device, &device); if (rc) return rc;
     DeviceGuard guard(device);
     if (!guard.ok) return fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", device);
@@ -1456,6 +1476,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         for (int k = 0; k < 3; ++k) { bp.centroid[k] = 0.5f * (b.lo[k] + b.hi[k]); max_abs = std::max(max_abs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))); }
         bprims.push_back(bp);
     }
+    lap("flatten prims + materials");
     // Scene-spanning primitives leave the BVH for the up-front list (DeviceScene::top_prims):
     // a box whose surface area is >= 30 % of the whole scene's is met by nearly every ray.
     DeviceScene ds_top{};
@@ -1497,6 +1518,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
     }
 
+    lap(use_lbvh ? "top list + padding" : "top list + padding + host SAH");
     std::vector<TexRec> tex(d->n_textures);
     for (uint32_t t = 0; t < d->n_textures; ++t) {
         const B200rtTexture& x = d->textures[t];
@@ -1524,7 +1546,8 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     // child (lo > hi) gets h = -1: near > far on every axis, never entered.
     const size_t n_nodes = use_lbvh ? lbvh_prims.size() - 1 : nodes.size();
     std::vector<BvhNode> cnodes(nodes.size());
-    for (size_t i = 0; i < nodes.size(); ++i) {
+#pragma omp parallel for schedule(static) if (nodes.size() >= 65536)
+    for (long long i = 0; i < (long long)nodes.size(); ++i) {
         const float* q = reinterpret_cast<const float*>(&nodes[i]);
         float* o = reinterpret_cast<float*>(&cnodes[i]);
         for (int ch = 0; ch < 2; ++ch) {
@@ -1541,6 +1564,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         }
         o[12] = q[12]; o[13] = q[13]; o[14] = q[14]; o[15] = q[15];
     }
+    lap("centre/half-extent nodes");
     Arena arena;
     size_t off_nodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(nodes);
     size_t off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
@@ -1548,12 +1572,13 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     // images: RGB8 -> RGBA8 so a texel is one 4-byte load
     std::vector<ImageRec> images(d->n_images);
     std::vector<size_t> off_img(d->n_images);
+    std::vector<std::vector<uchar4>> rgba(d->n_images);
     for (uint32_t i = 0; i < d->n_images; ++i) {
         const B200rtImage& im = d->images[i];
         size_t n = (size_t)im.width * im.height;
-        off_img[i] = arena.reserve(n * sizeof(uchar4));
-        uchar4* rgba = reinterpret_cast<uchar4*>(arena.host.data() + off_img[i]);
-        for (size_t k = 0; k < n; ++k) rgba[k] = make_uchar4(im.rgb8[3 * k], im.rgb8[3 * k + 1], im.rgb8[3 * k + 2], 255);
+        rgba[i].resize(n);
+        for (size_t k = 0; k < n; ++k) rgba[i][k] = make_uchar4(im.rgb8[3 * k], im.rgb8[3 * k + 1], im.rgb8[3 * k + 2], 255);
+        off_img[i] = arena.put(rgba[i]);
         images[i].width = im.width; images[i].height = im.height; images[i].pad = 0;
     }
     std::vector<PerlinRec> perlin(d->n_perlin);
@@ -1562,18 +1587,19 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         memcpy(perlin[i].perm_x, d->perlin[i].perm_x, 256); memcpy(perlin[i].perm_y, d->perlin[i].perm_y, 256); memcpy(perlin[i].perm_z, d->perlin[i].perm_z, 256);
     }
     size_t off_perlin = arena.put(perlin);
-    size_t off_images = arena.reserve(images.size() * sizeof(ImageRec));
+    size_t off_images = arena.put(images);      // the texel pointers are filled in below, before the upload
+    lap("lay out arena");
     uint8_t* dbase = nullptr;
     {
-        cudaError_t e = cudaMalloc(&dbase, arena.host.size());
-        if (e != cudaSuccess) return bail(fail(B200RT_ENOMEM, "scene arena (%zu B): %s", arena.host.size(), cudaGetErrorString(e)));
+        cudaError_t e = cudaMalloc(&dbase, arena.total);
+        if (e != cudaSuccess) return bail(fail(B200RT_ENOMEM, "scene arena (%zu B): %s", arena.total, cudaGetErrorString(e)));
         sc->allocs.push_back(dbase);
         for (uint32_t i = 0; i < d->n_images; ++i) images[i].texels = reinterpret_cast<const uchar4*>(dbase + off_img[i]);
-        if (!images.empty()) memcpy(arena.host.data() + off_images, images.data(), images.size() * sizeof(ImageRec));
-        e = cudaMemcpy(dbase, arena.host.data(), arena.host.size(), cudaMemcpyHostToDevice);
+        e = arena.upload(dbase);
         if (e != cudaSuccess) return bail(fail(B200RT_ECUDA, "scene upload: %s", cudaGetErrorString(e)));
-        sc->info.device_bytes = arena.host.size();
+        sc->info.device_bytes = arena.total;
     }
+    lap("cudaMalloc + H2D");
     sc->ds.nodes = reinterpret_cast<const BvhNode*>(dbase + off_nodes);
     sc->ds.cnodes = reinterpret_cast<const BvhNode*>(dbase + off_cnodes);
     if (use_lbvh) {
@@ -1583,6 +1609,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         if (depth > 60) return bail(fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack (B200RT_BUILDER=sah builds a shallower tree)", depth));
         bvh.depth = depth;
         sc->info.bvh_build_ms = ms; sc->info.bvh_builder = 1;
+        lap("device LBVH (incl. its uploads)");
     } else { sc->info.bvh_build_ms = host_build_ms; sc->info.bvh_builder = 0; }
     sc->ds.geom = reinterpret_cast<const GeomRec*>(dbase + off_geom);
     sc->ds.mats = reinterpret_cast<const MatRec*>(dbase + off_mats);

@@ -155,25 +155,28 @@ inline cudaError_t build(const std::vector<BuildPrim>& prims, const HostBox& bou
         hp[i].lo = make_float4(p.box.lo[0], p.box.lo[1], p.box.lo[2], codef);
         hp[i].hi = make_float4(p.box.hi[0], p.box.hi[1], p.box.hi[2], 0.f);
     }
-    PrimBox* d_prims = nullptr; unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
-    int2* d_children = nullptr; int *d_pi = nullptr, *d_pl = nullptr; SubBox* d_sub = nullptr; unsigned int* d_arr = nullptr; void* d_tmp = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaError_t e = cudaSuccess;
-    auto cleanup = [&]() {
-        cudaFree(d_prims); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_children); cudaFree(d_pi); cudaFree(d_pl);
-        cudaFree(d_sub); cudaFree(d_arr); cudaFree(d_tmp);
-        if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1);
-    };
-#define LBVH_TRY(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
-    LBVH_TRY(cudaMalloc(&d_prims, (size_t)n * sizeof(PrimBox)));
-    LBVH_TRY(cudaMalloc(&d_keys, (size_t)n * 8)); LBVH_TRY(cudaMalloc(&d_keys2, (size_t)n * 8));
-    LBVH_TRY(cudaMalloc(&d_vals, (size_t)n * 4)); LBVH_TRY(cudaMalloc(&d_vals2, (size_t)n * 4));
-    LBVH_TRY(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
-    LBVH_TRY(cudaMalloc(&d_pi, (size_t)(n - 1) * 4)); LBVH_TRY(cudaMalloc(&d_pl, (size_t)n * 4));
-    LBVH_TRY(cudaMalloc(&d_sub, (size_t)(n - 1) * sizeof(SubBox))); LBVH_TRY(cudaMalloc(&d_arr, (size_t)(n - 1) * 4));
+    // one scratch allocation carved into the builder's arrays (a dozen cudaMalloc/cudaFree pairs cost more than the build)
     size_t tmp_bytes = 0;
-    LBVH_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 63));
-    LBVH_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 63);
+    if (e != cudaSuccess) return e;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+    const size_t o_prims = carve((size_t)n * sizeof(PrimBox)), o_keys = carve((size_t)n * 8), o_keys2 = carve((size_t)n * 8), o_vals = carve((size_t)n * 4),
+                 o_vals2 = carve((size_t)n * 4), o_children = carve((size_t)(n - 1) * sizeof(int2)), o_pi = carve((size_t)(n - 1) * 4), o_pl = carve((size_t)n * 4),
+                 o_sub = carve((size_t)(n - 1) * sizeof(SubBox)), o_arr = carve((size_t)(n - 1) * 4), o_tmp = carve(tmp_bytes);
+    uint8_t* base = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() { cudaFree(base); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); };
+#define LBVH_TRY(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return e; } } while (0)
+    LBVH_TRY(cudaMalloc(&base, off));
+    PrimBox* d_prims = reinterpret_cast<PrimBox*>(base + o_prims);
+    unsigned long long *d_keys = reinterpret_cast<unsigned long long*>(base + o_keys), *d_keys2 = reinterpret_cast<unsigned long long*>(base + o_keys2);
+    uint32_t *d_vals = reinterpret_cast<uint32_t*>(base + o_vals), *d_vals2 = reinterpret_cast<uint32_t*>(base + o_vals2);
+    int2* d_children = reinterpret_cast<int2*>(base + o_children);
+    int *d_pi = reinterpret_cast<int*>(base + o_pi), *d_pl = reinterpret_cast<int*>(base + o_pl);
+    SubBox* d_sub = reinterpret_cast<SubBox*>(base + o_sub);
+    unsigned int* d_arr = reinterpret_cast<unsigned int*>(base + o_arr);
+    void* d_tmp = base + o_tmp;
     LBVH_TRY(cudaMemcpy(d_prims, hp.data(), (size_t)n * sizeof(PrimBox), cudaMemcpyHostToDevice));
     LBVH_TRY(cudaEventCreate(&e0)); LBVH_TRY(cudaEventCreate(&e1));
     LBVH_TRY(cudaEventRecord(e0));
