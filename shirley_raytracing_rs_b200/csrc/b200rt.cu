@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant
     }
 }
 
-constexpr uint32_t RAYQ_SLOTS = 64, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + stream, tile pixel
+constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + stream, tile pixel
 
 // Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
 // result does not depend on which lane traced which sample, nor on scheduling or sharding.
@@ -361,8 +361,10 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             const uint32_t want = (uint32_t)__popc(want_m);
             if (q_count < want && next_item < n_items) {           // warp-uniform
                 __syncwarp();
+                // top the ring up to 32 entries: the first (32 - q_count) lanes generate
+                const uint32_t n_new = min(RAYQ_SLOTS - q_count, n_items - next_item);
                 uint32_t item = next_item + (uint32_t)lane;
-                if (item < n_items) {
+                if ((uint32_t)lane < n_new) {
                     uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
                     uint32_t kth = item - sidx * nv;
                     uint32_t qpl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
@@ -379,7 +381,6 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                     rayq[4 * RAYQ_SLOTS + slot] = __float_as_uint(qd.y); rayq[5 * RAYQ_SLOTS + slot] = __float_as_uint(qd.z);
                     rayq[6 * RAYQ_SLOTS + slot] = qr.state; rayq[7 * RAYQ_SLOTS + slot] = qr.inc; rayq[8 * RAYQ_SLOTS + slot] = qpl;
                 }
-                uint32_t n_new = min(32u, n_items - next_item);
                 next_item += n_new; q_count += n_new;
                 __syncwarp();
             }
