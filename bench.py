@@ -359,7 +359,9 @@ def main():
             cores = os.cpu_count() or 1
             o.render(cam, 1, max_depth=DEPTH, seed=5, threads=cores)     # warm
             _, ost = o.render(cam, args.cpu_baseline_spp, max_depth=DEPTH, seed=6, threads=cores)
+            _, o1 = o.render(cam, 2, max_depth=DEPTH, seed=7, threads=1)   # the reference's --single-threaded twin (src/main.rs:97-112), 2 spp
             line["cpu_baseline"] = {"value": ost.rays / ost.seconds / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                    "single_thread_value": o1.rays / o1.seconds / 1e6,
                                     "sample": f"{W}x{H} full frame at {args.cpu_baseline_spp} spp (of {args.spp}), f64 oracle, OpenMP dynamic,1 over scanlines, {ost.seconds:.1f} s",
                                     "pops_per_ray": ost.pops / ost.rays, "leaf_tests_per_ray": ost.leaf_tests / ost.rays}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
