@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=16, help="spp of the bounded CPU sample per step")
     ap.add_argument("--cpu-baseline-spp", type=int, default=128, help="bounded CPU sample: ~10-30 s of host work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-barrier", default="flags", choices=["flags", "nccl"],
+                    help="--combine peer: order the ranks with flags in peer memory (default) or a one-element NCCL all_reduce")
     ap.add_argument("--combine", default="peer", choices=["peer", "nccl"],
                     help="N > 1: fused peer-memory reduce+resolve kernel over NVLink (default) or NCCL reduce then resolve on rank 0")
     args = ap.parse_args()
@@ -194,7 +196,7 @@ def main():
     peer = None
     if world > 1 and args.combine == "peer":
         from shirley_raytracing_rs_b200.sharding import PeerFrame
-        peer = PeerFrame(W, H, local_rank)               # IPC-shared accumulation buffers + the frame on rank 0
+        peer = PeerFrame(W, H, local_rank, barrier=args.peer_barrier)   # IPC-shared accumulation buffers, flags, the frame on rank 0
         accum = peer.accum()
     else:
         accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
@@ -217,6 +219,8 @@ def main():
     def frame(step, count=False):
         """One step with the scene resident in HBM: render (+ at N > 1 the cross-GPU sum and resolve)."""
         p = params(step, count)
+        if peer is not None:
+            peer.begin_frame(sptr)
         F.check(lib.b200rt_render_device(dscene, C.byref(cam), C.byref(p), accum.data_ptr(), sptr))
         if world > 1:
             combine()
@@ -259,7 +263,9 @@ def main():
         step_ms.append(e0.elapsed_time(e1)); kernel_ms.append(st.kernel_ms)
         rays += st.rays; launches += st.launches
         if world > 1:
-            launches += 1 if (peer is not None or rank == 0) else 0   # resolve_peers_kernel on every rank / resolve_kernel on rank 0
+            # peer: resolve_peers_kernel + the flag kernels (signal, wait, signal, and the next frame's wait) on every rank;
+            # nccl: resolve_kernel on rank 0
+            launches += (5 if args.peer_barrier == "flags" else 1) if peer is not None else (1 if rank == 0 else 0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -286,11 +292,13 @@ def main():
                 F.check(lib.b200rt_render_rgb8(h, C.byref(cam), C.byref(p), rgb_t.data_ptr(), None, C.byref(st)))
             else:
                 p = params(step)
+                if peer is not None:
+                    peer.begin_frame(sptr)
                 F.check(lib.b200rt_render_device(h, C.byref(cam), C.byref(p), accum.data_ptr(), sptr))
                 combine()
                 F.check(lib.b200rt_render_device_finish(h, sptr, C.byref(st)))
                 if rank == 0:
-                    rgb_t.copy_(peer.frame() if peer is not None else frame_dev, non_blocking=True)
+                    rgb_t.copy_(peer.frame(sptr) if peer is not None else frame_dev, non_blocking=True)
                 torch.cuda.synchronize()
         finally:
             lib.b200rt_scene_destroy(h)
@@ -366,6 +374,8 @@ def main():
                                     "pops_per_ray": ost.pops / ost.rays, "leaf_tests_per_ray": ost.leaf_tests / ost.rays}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if peer is not None:
+        if peer.timed_out():
+            log(f"[rank {rank}] WARNING: a peer flag wait timed out (rank {peer.timed_out() - 1} never arrived)")
         peer.close()
     if world > 1:
         dist.destroy_process_group()

@@ -271,6 +271,20 @@ int  b200rt_peer_buffer_create(int device, size_t bytes, void** d_ptr, uint8_t h
 int  b200rt_peer_buffer_open(int device, const uint8_t handle[B200RT_PEER_HANDLE_BYTES], void** d_ptr);
 int  b200rt_peer_buffer_close(int device, void* d_ptr);      /* a pointer from _open  */
 int  b200rt_peer_buffer_destroy(int device, void* d_ptr);    /* a pointer from _create */
+/* Stream-ordered cross-GPU barrier over peer memory, no library collective: each rank creates a flag array of
+ * B200RT_PEER_FLAG_BYTES with b200rt_peer_buffer_create (zeroed) and opens its peers'.  _signal writes `epoch`
+ * into slot [slot][my_rank] of EVERY rank's array (system-scope release after the stream's earlier work);
+ * _wait blocks the stream until all ranks' epochs in [slot] of the OWN array reached `epoch` (acquire).
+ * slot 0: "my accumulation buffer is complete" (before the fused resolve), slot 1: "I have finished reading"
+ * (before the next frame overwrites the buffers, and before rank 0 reads the assembled frame).  A peer that
+ * never arrives ends the wait after timeout_ms (0 = 10 s) and is reported by b200rt_peer_timed_out
+ * (*out = 1 + rank, 0 = none) instead of hanging the device. */
+#define B200RT_PEER_FLAG_BYTES 256
+int  b200rt_peer_signal_device(uint32_t* const* d_flag_arrays, uint32_t n_peers, uint32_t my_rank,
+                               uint32_t slot, uint32_t epoch, void* cuda_stream);
+int  b200rt_peer_wait_device(uint32_t* d_my_flags, uint32_t n_peers, uint32_t slot, uint32_t epoch,
+                             uint32_t timeout_ms, void* cuda_stream);
+int  b200rt_peer_timed_out(const uint32_t* d_my_flags, uint32_t* out);
 int  b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers,
                                       uint32_t width, uint32_t height, uint32_t samples,
                                       uint32_t row_begin, uint32_t row_end,

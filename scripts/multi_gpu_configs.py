@@ -43,6 +43,7 @@ def run(name, scene, cam, total_spp, mode, png):
         sr = sample_ranges(total_spp, world)[rank]
         p = F.RenderParams(samples=sr.samples, sample_offset=sr.sample_offset, max_depth=50, seed=11, device=-1)
     def frame():
+        pf.begin_frame()
         F.check(lib.b200rt_render_device(h, C.byref(cam), C.byref(p), pf.accum_ptr, None))
         pf.combine(total_spp)
         st = F.Stats()

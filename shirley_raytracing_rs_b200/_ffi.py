@@ -131,6 +131,9 @@ SIGNATURES = {
     "b200rt_peer_buffer_open": (C.c_int, [C.c_int, C.c_void_p, _P(C.c_void_p)]),
     "b200rt_peer_buffer_close": (C.c_int, [C.c_int, C.c_void_p]),
     "b200rt_peer_buffer_destroy": (C.c_int, [C.c_int, C.c_void_p]),
+    "b200rt_peer_signal_device": (C.c_int, [_P(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "b200rt_peer_wait_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "b200rt_peer_timed_out": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "b200rt_resolve_peers_rgb8_device": (C.c_int, [_P(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                    C.c_void_p, C.c_void_p]),
     "b200rt_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]),

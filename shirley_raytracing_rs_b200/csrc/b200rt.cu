@@ -943,6 +943,34 @@ __global__ void resolve_peers_kernel(const __grid_constant__ PeerResolveArgs a) 
     }
 }
 
+
+// Cross-GPU ordering for the fused resolve without a library collective: every rank owns a small flag
+// array in peer-visible memory, [slot][rank] epochs.  signal = "my stream has reached this point" written
+// into every peer's array (release, system scope); wait = spin until all peers' epochs arrived (acquire).
+// slot 0 = "my accumulation buffer is complete", slot 1 = "I am done reading your buffer".
+constexpr uint32_t PEER_FLAG_STRIDE = 16;
+struct PeerSignalArgs { uint32_t* flags[MAX_PEERS]; uint32_t n_peers, my_rank, slot, epoch; };
+__global__ void peer_signal_kernel(const __grid_constant__ PeerSignalArgs a) {
+    uint32_t p = threadIdx.x;
+    if (p >= a.n_peers) return;
+    __threadfence_system();
+    uint32_t* dst = a.flags[p] + a.slot * PEER_FLAG_STRIDE + a.my_rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(a.epoch) : "memory");
+}
+__global__ void peer_wait_kernel(const uint32_t* my_flags, uint32_t n_peers, uint32_t slot, uint32_t epoch, unsigned long long timeout_ns, uint32_t* timed_out) {
+    uint32_t r = threadIdx.x;
+    if (r >= n_peers) return;
+    const uint32_t* src = my_flags + slot * PEER_FLAG_STRIDE + r;
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicExch(timed_out, 1u + r); break; }   // a missing peer must not hang the GPU: report and go on
+        __nanosleep(200);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // parity-hook kernels
 // ------------------------------------------------------------------------------------------
@@ -1777,6 +1805,29 @@ int b200rt_peer_buffer_destroy(int device, void* d_ptr) {
     int rc = resolve_device(device, &device); if (rc) return rc;
     DeviceGuard guard(device);
     CU(cudaFree(d_ptr));
+    return B200RT_OK;
+}
+
+int b200rt_peer_signal_device(uint32_t* const* d_flag_arrays, uint32_t n_peers, uint32_t my_rank, uint32_t slot, uint32_t epoch, void* cuda_stream) {
+    if (!d_flag_arrays || n_peers < 1 || n_peers > (uint32_t)MAX_PEERS || my_rank >= n_peers || slot > 1) return fail(B200RT_EINVAL, "bad argument");
+    PeerSignalArgs a{};
+    for (uint32_t p = 0; p < n_peers; ++p) { if (!d_flag_arrays[p]) return fail(B200RT_EINVAL, "flag array %u is NULL", p); a.flags[p] = d_flag_arrays[p]; }
+    a.n_peers = n_peers; a.my_rank = my_rank; a.slot = slot; a.epoch = epoch;
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(a);
+    CU(cudaGetLastError());
+    return B200RT_OK;
+}
+int b200rt_peer_wait_device(uint32_t* d_my_flags, uint32_t n_peers, uint32_t slot, uint32_t epoch, uint32_t timeout_ms, void* cuda_stream) {
+    if (!d_my_flags || n_peers < 1 || n_peers > (uint32_t)MAX_PEERS || slot > 1) return fail(B200RT_EINVAL, "bad argument");
+    // word 2 * stride of the flag array records a time-out (1 + the rank that never arrived)
+    peer_wait_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(d_my_flags, n_peers, slot, epoch, (unsigned long long)(timeout_ms ? timeout_ms : 10000) * 1000000ull,
+                                                            d_my_flags + 2 * PEER_FLAG_STRIDE);
+    CU(cudaGetLastError());
+    return B200RT_OK;
+}
+int b200rt_peer_timed_out(const uint32_t* d_my_flags, uint32_t* out) {
+    if (!d_my_flags || !out) return fail(B200RT_EINVAL, "NULL argument");
+    CU(cudaMemcpy(out, d_my_flags + 2 * PEER_FLAG_STRIDE, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return B200RT_OK;
 }
 

@@ -71,14 +71,19 @@ class PeerFrame:
     """Per-rank accumulation buffers visible to every rank of one node (CUDA IPC over NVLink)
     plus the RGB8 frame on `root`, for b200rt_resolve_peers_rgb8_device: the cross-GPU sum is
     fused into the resolve and every rank assembles its band of rows directly into the root's
-    frame (include/b200rt.h).  One process per GPU; handles travel over torch.distributed.
+    frame (include/b200rt.h).  One process per GPU; handles travel over torch.distributed once.
+    Per-frame ordering between the ranks is a flag barrier over the same peer memory
+    (b200rt_peer_signal_device / _wait_device): no library collective on the data path
+    (barrier="nccl" uses a one-element all_reduce instead, for comparison).
 
         pf = PeerFrame(W, H, device_index)
-        render into pf.accum_ptr ...; pf.combine(total_samples, stream_ptr)   # collective
-        frame = pf.frame()          # on root: (H, W, 3) uint8 torch tensor on the device
+        per frame:  pf.begin_frame(stream)            # peers have finished reading last frame's buffers
+                    render into pf.accum_ptr on `stream`
+                    pf.combine(total_samples, stream) # collective: sum + resolve of this rank's band into root's frame
+        frame = pf.frame(stream)                      # on root: (H, W, 3) uint8 torch tensor on the device
     """
 
-    def __init__(self, width: int, height: int, device: int, root: int = 0, group=None):
+    def __init__(self, width: int, height: int, device: int, root: int = 0, group=None, barrier: str = "flags"):
         import ctypes as C
         import torch
         import torch.distributed as dist
@@ -88,6 +93,9 @@ class PeerFrame:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 16:
             raise ValueError("at most 16 peers")
+        if barrier not in ("flags", "nccl"):
+            raise ValueError("barrier must be 'flags' or 'nccl'")
+        self.barrier = barrier
         lib = F.lib
         self._own = []
         def create(nbytes):
@@ -96,9 +104,10 @@ class PeerFrame:
             self._own.append(p)
             return p, bytes(h)
         acc_p, acc_h = create(width * height * 16)
+        flag_p, flag_h = create(256)
         rgb_p, rgb_h = create(width * height * 3) if self.rank == root else (None, None)
         handles = [None] * self.world
-        dist.all_gather_object(handles, (acc_h, rgb_h), group=group)
+        dist.all_gather_object(handles, (acc_h, rgb_h, flag_h), group=group)
         self._opened = []
         def open_(h):
             p, buf = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(h)
@@ -106,31 +115,67 @@ class PeerFrame:
             self._opened.append(p)
             return p
         self.accum_ptrs = [acc_p if r == self.rank else open_(handles[r][0]) for r in range(self.world)]
+        self.flag_ptrs = [flag_p if r == self.rank else open_(handles[r][2]) for r in range(self.world)]
         self.frame_ptr = rgb_p if self.rank == root else open_(handles[root][1])
-        self.accum_ptr = acc_p
+        self.accum_ptr, self.flag_ptr = acc_p, flag_p
         self._ptr_array = (C.c_void_p * self.world)(*[p.value for p in self.accum_ptrs])
+        self._flag_array = (C.c_void_p * self.world)(*[p.value for p in self.flag_ptrs])
         self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device))
         self.band = row_bands(height, self.world)[self.rank]
+        self.epoch = 0
+        self.timeout_ms = 10000
+        dist.barrier(group=group)          # every rank has opened every handle before any kernel touches a peer
+
+    # -- ordering ------------------------------------------------------------------------------------------
+    def _signal(self, slot, stream_ptr):
+        F = self._F
+        F.check(F.lib.b200rt_peer_signal_device(self._flag_array, self.world, self.rank, slot, self.epoch, stream_ptr))
+
+    def _wait(self, slot, stream_ptr):
+        F = self._F
+        F.check(F.lib.b200rt_peer_wait_device(self.flag_ptr, self.world, slot, self.epoch, self.timeout_ms, stream_ptr))
 
     def sync(self):
-        """Stream-ordered barrier: kernels enqueued after it start after every rank's earlier work."""
+        """Stream-ordered barrier through NCCL (barrier='nccl'): kernels enqueued after it start after every rank's earlier work."""
         self._dist.all_reduce(self._flag, group=self.group)
 
+    def begin_frame(self, stream_ptr=None):
+        """Before rendering into accum_ptr again: every peer has finished reading the previous frame's buffers."""
+        if self.barrier == "flags" and self.epoch > 0:
+            self._wait(1, stream_ptr)
+
     def combine(self, total_samples: int, stream_ptr=None):
-        """sync; resolve this rank's band from all ranks' buffers into the root's frame; sync."""
-        F, C = self._F, self._C
-        self.sync()
+        """Collective.  Orders this rank's render before the peers' reads, resolves this rank's band of rows from
+        all ranks' buffers into the root's frame, and publishes 'done reading'."""
+        F = self._F
+        self.epoch += 1
+        if self.barrier == "flags":
+            self._signal(0, stream_ptr)
+            self._wait(0, stream_ptr)
+        else:
+            self.sync()
         F.check(F.lib.b200rt_resolve_peers_rgb8_device(self._ptr_array, self.world, self.W, self.H, total_samples,
                                                       self.band[0], self.band[1], self.frame_ptr, stream_ptr))
-        self.sync()
+        if self.barrier == "flags":
+            self._signal(1, stream_ptr)
+        else:
+            self.sync()
 
     def accum(self):
         """This rank's accumulation buffer as an (H, W, 4) float32 torch tensor (no copy)."""
         return self._torch.as_tensor(_DevicePtr(self.accum_ptr.value, (self.H, self.W, 4), "<f4"), device=self._torch.device("cuda", self.device))
 
-    def frame(self):
-        """The assembled RGB8 frame, (H, W, 3) uint8, top row first (valid on every rank as a peer view)."""
+    def frame(self, stream_ptr=None):
+        """The assembled RGB8 frame, (H, W, 3) uint8, top row first; ordered after every rank's band (call after combine)."""
+        if self.barrier == "flags" and self.epoch > 0:
+            self._wait(1, stream_ptr)
         return self._torch.as_tensor(_DevicePtr(self.frame_ptr.value, (self.H, self.W, 3), "|u1"), device=self._torch.device("cuda", self.device))
+
+    def timed_out(self) -> int:
+        """0, or 1 + the rank a flag wait gave up on (a peer died or never called combine)."""
+        out = self._C.c_uint32()
+        self._F.check(self._F.lib.b200rt_peer_timed_out(self.flag_ptr, self._C.byref(out)))
+        return out.value
 
     def close(self):
         F = self._F

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, spp, out_path):
+def _worker(rank, world, port, spp, out_path, barrier):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -35,11 +35,12 @@ def _worker(rank, world, port, spp, out_path):
     scene = rt.Scene.named("random", seed=0xDEADBEEF)
     cam = rt.default_camera(300)
     W, H = cam.image_width, cam.image_height
-    pf = PeerFrame(W, H, rank)
+    pf = PeerFrame(W, H, rank, barrier=barrier)
     sr = weak_sample_range(spp, rank)
     frames = []
-    for rep in range(2):                                   # twice: buffers are reused across frames
-        p = F.RenderParams(samples=sr.samples, sample_offset=sr.sample_offset, max_depth=50, seed=5 + rep, device=-1)
+    for rep in range(3):                                   # several frames: buffers and flags are reused
+        pf.begin_frame()
+        p = F.RenderParams(samples=sr.samples, sample_offset=sr.sample_offset, max_depth=50, seed=4 + rep, device=-1)
         F.check(F.lib.b200rt_render_device(scene.device(rank), C.byref(cam), C.byref(p), pf.accum_ptr, None))
         pf.combine(spp * world)
         st = F.Stats()
@@ -47,22 +48,24 @@ def _worker(rank, world, port, spp, out_path):
         torch.cuda.synchronize()
         frames.append(pf.frame().cpu().numpy().copy())
     acc = pf.accum().cpu().numpy().copy()
+    assert pf.timed_out() == 0
     gathered = [None] * world
     dist.all_gather_object(gathered, acc)
     if rank == 0:
-        np.savez(out_path, frame0=frames[0], frame1=frames[1], **{f"acc{r}": gathered[r] for r in range(world)})
+        np.savez(out_path, frame0=frames[1], frame1=frames[2], **{f"acc{r}": gathered[r] for r in range(world)})
     pf.close()
     dist.destroy_process_group()
 
 
-def test_two_gpu_peer_resolve_matches_one_gpu(tmp_path, rt, gpu_required):
+@pytest.mark.parametrize("barrier", ["flags", "nccl"])
+def test_two_gpu_peer_resolve_matches_one_gpu(tmp_path, rt, gpu_required, barrier):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     world, spp = 2, 8
     out = str(tmp_path / "r0.npz")
-    mp.spawn(_worker, args=(world, _free_port(), spp, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), spp, out, barrier), nprocs=world, join=True)
     got = np.load(out)
     scene = rt.Scene.named("random", seed=0xDEADBEEF)
     cam = rt.default_camera(300)
