@@ -831,20 +831,39 @@ struct HitArgs {
     int32_t* ids; B200rtHit* hits; Counters* counters;
 };
 
-template <class Acc, bool COUNT>
+// K1 runs the SAME traversal code as the render kernel (per-segment set-up with shared IEEE reciprocals, up-front
+// primitives, trav_inner_s / trav_leaf_s over the sentinel stack; FAST = centre/half-extent boxes) so that the
+// bit-exact id / t / normal parity tests exercise the product's traversal, not a parity-only twin.
+template <class Acc, bool COUNT, bool FAST>
 __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constant__ HitArgs a) {
     extern __shared__ float4 smem[];
     int* stack_base;
     Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
     int* stack = stack_base + threadIdx.x;
+    stack[0] = B200RT_TRAV_DONE;
+    const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
     TravCounters tc; tc.nodes = 0; tc.prims = 0;
-    const TopPrims top = top_of(a.scene);
     unsigned long long nr = 0;
     for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BLOCK) {
         B200rtRay in = a.rays[i];
-        RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
+        RayF ray;
+        ray.o = f3(in.ox, in.oy, in.oz); ray.d = f3(in.dx, in.dy, in.dz);
+        float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
+        ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
+        ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
+        ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
         Closest c; c.t = a.t_max; c.code = -1; c.face = 0;
-        closest_hit<COUNT>(ray, acc, top, stack, BLOCK, a.t_min, c, tc);
+#pragma unroll 1
+        for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
+            if (COUNT) tc.prims++;
+            hit_leaf(ray, acc, a.scene.top_prims[k], a.t_min, c, &inv_e);
+        }
+        int node = 0;
+        uint32_t top_sp = stack_s + BLOCK * 4;
+        while (node != B200RT_TRAV_DONE) {
+            while (node >= 0 && node != B200RT_TRAV_DONE) trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
+            if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
+        }
         ++nr;
         int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_LEAF_ID_MASK);
         a.ids[i] = id;
@@ -1914,7 +1933,14 @@ int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, 
         CU(cudaEventRecord(e1));
         return B200RT_OK;
     };
-    if (plan.all_in_smem) rc = go(closest_hit_kernel<SmemAcc, true>); else rc = go(closest_hit_kernel<GmemAcc, true>);
+    // the one-FMA / centre-form slab tests are conservative only while |origin| * eps stays below the box padding (as in launch_render)
+    float max_origin = sc->max_abs_coord;
+    for (size_t i = 0; i < n; ++i) max_origin = std::max(max_origin, std::max(std::fabs(rays[i].ox), std::max(std::fabs(rays[i].oy), std::fabs(rays[i].oz))));
+    const char* fs = getenv("B200RT_FAST_SLAB");
+    bool fast = sc->box_pad >= 4.0f * 1.1920929e-7f * max_origin && !(fs && atoi(fs) == 0);
+    if (fast) a.scene.nodes = sc->ds.cnodes;
+    if (plan.all_in_smem) rc = fast ? go(closest_hit_kernel<SmemAcc, true, true>) : go(closest_hit_kernel<SmemAcc, true, false>);
+    else rc = fast ? go(closest_hit_kernel<GmemAcc, true, true>) : go(closest_hit_kernel<GmemAcc, true, false>);
     if (rc == B200RT_OK) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "closest_hit: %s", cudaGetErrorString(e));

@@ -431,3 +431,29 @@ def test_device_built_bvh_gives_the_same_hits(rt, po, gpu_required, monkeypatch,
     assert np.array_equal(ids, ids2)
     img_s, st_s = rt.render(s2, cam, samples=4, seed=3)
     assert np.array_equal(img_l, img_s) and st_l.rays == st_s.rays
+
+
+def test_exact_slab_path_gives_the_same_hits(rt, po, weekend, gpu_required, monkeypatch):
+    """B200RT_FAST_SLAB=0 runs Aabb::hit2's exact arithmetic on the (lo, hi) boxes instead of the centre/half-extent
+    three-FMA form: boxes only cull, so ids / t / normals are identical either way and images agree to rounding."""
+    rays = fixed_ray_set(rt, po, weekend, width=200)
+    ids_f, hits_f, st_f = rt.closest_hit(weekend, rays, 0.001, INF)
+    cam = rt.default_camera(120)
+    img_f, _ = rt.render(weekend, cam, samples=4, seed=8)
+    monkeypatch.setenv("B200RT_FAST_SLAB", "0")
+    ids_e, hits_e, st_e = rt.closest_hit(weekend, rays, 0.001, INF)
+    img_e, _ = rt.render(weekend, cam, samples=4, seed=8)
+    assert np.array_equal(ids_f, ids_e)
+    hit = ids_f >= 0
+    assert np.array_equal(hits_f["t"][hit], hits_e["t"][hit]) and np.array_equal(hits_f["n"][hit], hits_e["n"][hit])
+    # the two kernel instantiations may contract a * b + c differently in the SHADING arithmetic (plain operators):
+    # a last-bit difference in a scattered direction can grow over later bounces, so a few pixels differ visibly
+    diff = np.abs(img_f - img_e)
+    assert (diff > 1e-5 * np.maximum(np.abs(img_e), 1.0)).mean() < 0.02 and diff.max() < 0.25, ((diff > 1e-5).mean(), diff.max())
+    want = po.closest_hit_gpu32(weekend.desc, rays, 0.001, INF)
+    assert np.array_equal(ids_e, want["id"])
+    # far-away origins switch the fast form off by themselves (|origin| * eps must stay below the box padding)
+    monkeypatch.delenv("B200RT_FAST_SLAB")
+    far = rays[:2000].copy(); far[:, :3] += np.float32(3.0e5)
+    ids_far, _, _ = rt.closest_hit(weekend, far, 0.001, INF)
+    assert np.array_equal(ids_far, po.closest_hit_gpu32(weekend.desc, far, 0.001, INF)["id"])
