@@ -1005,28 +1005,37 @@ __global__ void aabb_hit_kernel(const float* __restrict__ boxes6, const B200rtRa
 
 struct ScatterArgs { DeviceScene scene; const B200rtRay* rays; const B200rtHit* hits; size_t n; RngKeys keys; B200rtScatter* out; };
 __global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
+    // The render kernel's own shading sequence: shade_prepare -> warp-cooperative Perlin -> shade_finish.
+    // No early return: coop_turbulence is a warp collective (the grid is rounded up to whole warps).
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const bool in_range = i < a.n;
     GmemAcc acc;
     acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
     acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
     acc.top = nullptr; acc.n_top = 0;
-    B200rtRay in = a.rays[i];
-    B200rtHit hi = a.hits[i];
+    B200rtRay in{}; B200rtHit hi{}; hi.id = -1;
+    if (in_range) { in = a.rays[i]; hi = a.hits[i]; }
     B200rtScatter out; memset(&out, 0, sizeof out);
-    if (hi.id >= 0 && (uint32_t)hi.id < a.scene.n_prims) {
-        RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
-        // rebuild the device hit record from the caller's record; u,v come from the geometry
-        HitRec h;
-        h.id = hi.id; h.t = hi.t; h.p = f3(hi.p[0], hi.p[1], hi.p[2]); h.n = f3(hi.n[0], hi.n[1], hi.n[2]);
-        h.front = hi.front_face != 0;
-        h.n_out = h.front ? h.n : -h.n;
-        h.type = 0xffu; h.face = 0;
-        h.has_uv = true; h.uv_u = hi.u; h.uv_v = hi.v;   // Texture::value(record.u, record.v, ..), lambertian.rs:34
+    const bool valid = in_range && hi.id >= 0 && (uint32_t)hi.id < a.scene.n_prims;
+    RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
+    // rebuild the device hit record from the caller's record; u,v come from the geometry
+    HitRec h;
+    h.id = hi.id; h.t = hi.t; h.p = f3(hi.p[0], hi.p[1], hi.p[2]); h.n = f3(hi.n[0], hi.n[1], hi.n[2]);
+    h.front = hi.front_face != 0;
+    h.n_out = h.front ? h.n : -h.n;
+    h.type = 0xffu; h.face = 0;
+    h.has_uv = true; h.uv_u = hi.u; h.uv_v = hi.v;   // Texture::value(record.u, record.v, ..), lambertian.rs:34
+    ShadePrep sp; sp.tex.need_perlin = false; sp.tex.perlin_idx = 0; sp.tex.perlin_scale = 0.f; sp.tex.rgb = f3(0, 0, 0);
+    if (valid) sp = shade_prepare(a.scene, acc, h);
+    const bool need = valid && sp.tex.need_perlin;
+    float turb = 0.0f;
+    if (a.scene.perlin != nullptr && __any_sync(0xffffffffu, need)) turb = coop_turbulence(a.scene.perlin, need, h.p, sp.tex.perlin_idx);
+    if (valid) {
         Rng rng; rng.init(a.keys, (uint32_t)i, 0u);
         uint32_t s0 = rng.state;
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
-        ShadeOut so = shade(a.scene, acc, ray, h, rng, atten, emit);
+        float3 albedo = sp.tex.need_perlin ? marble(sp.tex.perlin_scale, h.p, turb) : sp.tex.rgb;
+        ShadeOut so = shade_finish(ray, h, sp.m, albedo, rng, atten, emit);
         out.ray.ox = so.o.x; out.ray.oy = so.o.y; out.ray.oz = so.o.z;
         out.ray.dx = so.d.x; out.ray.dy = so.d.y; out.ray.dz = so.d.z;
         out.attenuation[0] = atten.x; out.attenuation[1] = atten.y; out.attenuation[2] = atten.z;
@@ -1037,7 +1046,7 @@ __global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
         while (st != rng.state && k < 4096) { st = st * 747796405u + rng.inc; ++k; }
         out.draws = k;
     }
-    a.out[i] = out;
+    if (in_range) a.out[i] = out;
 }
 
 __global__ void camera_rays_kernel(DeviceCamera cam, const float* __restrict__ xy, size_t n, RngKeys keys, B200rtRay* out) {
@@ -1052,19 +1061,25 @@ __global__ void camera_rays_kernel(DeviceCamera cam, const float* __restrict__ x
 
 struct TexArgs { DeviceScene scene; int32_t tex; const float* uvp5; size_t n; float* out; };
 __global__ void texture_value_kernel(const __grid_constant__ TexArgs a) {
+    // Texture::value the way the render kernel evaluates it: descent per lane, marble turbulence by the whole warp.
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    const bool in_range = i < a.n;
     GmemAcc acc;
     acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
     acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
     acc.top = nullptr; acc.n_top = 0;
-    const float* q = a.uvp5 + i * 5;
+    const float* q = a.uvp5 + (in_range ? i : 0) * 5;
     HitRec h;
     h.id = -1; h.type = 0xffu; h.face = 0; h.t = 0; h.front = true;
     h.p = f3(q[2], q[3], q[4]); h.n = f3(0, 1, 0); h.n_out = h.n;
     h.has_uv = true; h.uv_u = q[0]; h.uv_v = q[1];
-    float3 c = texture_value(acc, a.scene.images, a.scene.perlin, a.tex, h);
-    a.out[i * 3 + 0] = c.x; a.out[i * 3 + 1] = c.y; a.out[i * 3 + 2] = c.z;
+    TexResult r; r.need_perlin = false; r.perlin_idx = 0; r.perlin_scale = 0.f; r.rgb = f3(0, 0, 0);
+    if (in_range) r = texture_descend(acc, a.scene.images, a.tex, h);
+    const bool need = in_range && r.need_perlin;
+    float turb = 0.0f;
+    if (a.scene.perlin != nullptr && __any_sync(0xffffffffu, need)) turb = coop_turbulence(a.scene.perlin, need, h.p, r.perlin_idx);
+    float3 c = r.need_perlin ? marble(r.perlin_scale, h.p, turb) : r.rgb;
+    if (in_range) { a.out[i * 3 + 0] = c.x; a.out[i * 3 + 1] = c.y; a.out[i * 3 + 2] = c.z; }
 }
 
 __global__ void rng_kernel(RngKeys keys, uint32_t ka, uint32_t kb, size_t n, float* out) {
