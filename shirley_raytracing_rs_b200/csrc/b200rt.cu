@@ -239,7 +239,7 @@ __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v
     // 2^-32 fixed point; non-finite contributions are dropped (a NaN sample would blacken the
     // reference's pixel; here it contributes nothing)
     const float S = 4294967296.0f;
-    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+    if (fabsf(v.x + v.y + v.z) <= 3.0e38f) {   // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative)
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
