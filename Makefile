@@ -30,7 +30,7 @@ cli: ray-cli
 ray-cli: $(PKG)/cli/ray_cli.cpp $(LIB) $(HOST_HDRS)
 	$(HOSTCXX) $(CXXFLAGS) -o $@ $< -L$(PKG) -lb200rt -Wl,-rpath,'$$ORIGIN/$(PKG)'
 
-build/b200rt.o: $(CSRC)/b200rt.cu $(CSRC)/rt_device.cuh $(CSRC)/bvh_build.hpp $(CSRC)/lbvh.cuh include/b200rt.h
+build/b200rt.o: $(CSRC)/b200rt.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/bvh_build.hpp include/b200rt.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/ptxas_b200rt.log || (cat build/ptxas_b200rt.log; false)
 	@grep -E "error|warning: .*spill|bytes spill" build/ptxas_b200rt.log | grep -v "0 bytes spill" | head -20 || true

@@ -1,12 +1,14 @@
-// b200rt.cu — sm_100a kernels and the C ABI of include/b200rt.h.
+// b200rt.cu — the C ABI of include/b200rt.h: scene flattening and upload, BVH build, launch plumbing.
 //
-// Kernels (SURVEY.md §2 "new kernels"):
-//   K2 path_trace_kernel    render_scanline + ray_color     (render.rs:17-70)
-//   K1 closest_hit_kernel   BboxTree::hit_workspace batch   (bvh/bbox_tree.rs:56-91)
-//   K3 resolve_kernel       to_image + Color::to_pixel      (image.rs:34-40, core/color.rs:31-38)
-//   K4 scatter_kernel       MaterialType::scatter/emitted   (material_type.rs:50-79)
-//   + small parity hooks (aabb_hit, camera_rays, texture_value, rng) and an FFMA-chain
-//   microbenchmark that measures the FP32 issue ceiling used as the roofline denominator.
+// Device code (SURVEY.md §2 "new kernels") lives in the headers this file includes:
+//   rt_device.cuh        data layout, math, RNG, intersection, traversal steps, shading, textures
+//   render_kernel.cuh    K2 path_trace_kernel_v2   render_scanline + ray_color     (render.rs:17-70)
+//   render_variants.cuh  K2 design experiments v1 / v3, selectable with B200RT_KERNEL
+//   aux_kernels.cuh      K1 closest_hit_kernel     BboxTree::hit_workspace batch   (bvh/bbox_tree.rs:56-91)
+//                        K3 resolve_kernel (+ resolve_peers_kernel, flag barrier)  (image.rs:34-40, core/color.rs:31-38)
+//                        K4 scatter / camera_rays / texture_value / aabb_hit / rng parity hooks, FFMA-chain microbenchmark
+//   lbvh.cuh             K5 linear BVH built on the device                         (bvh/bbox_tree/constructor.rs:9-212)
+//   bvh_build.hpp        host binned-SAH builder
 // No tensor cores: nothing on this path is a dense contraction.  No CPU fallback.
 #include <cuda_runtime.h>
 
@@ -45,1065 +47,12 @@ static int fail(int code, const char* fmt, ...) {
                                            "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// ------------------------------------------------------------------------------------------
-// kernel arguments
-// ------------------------------------------------------------------------------------------
-constexpr int BLOCK = 256;          // threads per CTA (8 warps)
-constexpr size_t LBVH_AUTO_MIN = 262144;   // primitives from which scene_create builds the tree on the device
-constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
-
-struct SmemPlan {
-    uint32_t all_in_smem;           // 1: nodes + geom + mats + tex all staged (SmemAcc)
-    uint32_t n_top;                 // nodes staged when !all_in_smem
-    uint32_t stack_depth;           // entries per thread
-    uint32_t bytes;                 // dynamic shared memory per CTA
-};
-
-struct Counters {                   // device-side, one per in-flight render
-    unsigned long long rays, paths, nodes, prims, exhausted;
-    unsigned int tile_counter, pad;
-    unsigned long long diag[8];
-};
-
-struct RenderArgs {
-    DeviceScene scene;
-    DeviceCamera cam;
-    SmemPlan plan;
-    RngKeys keys;
-    uint32_t samples, sample_offset, max_depth;
-    uint32_t row_begin, row_end;
-    uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
-    uint32_t shard_count, shard_index;
-    uint32_t accumulate;
-    uint32_t trav_threshold;                    // v2: leave the traversal loop when fewer lanes than this still traverse
-    uint32_t wf_inner, wf_fetch, wf_park;       // v3 thresholds (see path_trace_kernel_v3)
-    float4* accum;
-    Counters* counters;
-};
-
-__device__ __forceinline__ TopPrims top_of(const DeviceScene& s) {
-    TopPrims t; t.n = s.n_top_prims;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) t.code[k] = s.top_prims[k];
-    return t;
-}
-
-// Stage the scene (or the top of the BVH) into shared memory and set up the accessor.
-// Shared layout: [nodes][geom][mats][tex][stack: stack_depth x BLOCK ints]
-template <class Acc> struct Stager;
-template <> struct Stager<SmemAcc> {
-    static __device__ __forceinline__ SmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
-        uint32_t n_nodes4 = s.n_nodes * 4, n_geom4 = s.n_prims * 2, n_mat4 = s.n_prims * 2, n_tex4 = s.n_tex * 2;
-        float4* nodes = smem;
-        float4* geom = nodes + n_nodes4;
-        float4* mats = geom + n_geom4;
-        float4* tex = mats + n_mat4;
-        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
-        const float4* gg = reinterpret_cast<const float4*>(s.geom);
-        const float4* gm = reinterpret_cast<const float4*>(s.mats);
-        const float4* gt = reinterpret_cast<const float4*>(s.tex);
-        for (uint32_t i = threadIdx.x; i < n_nodes4; i += blockDim.x) nodes[i] = __ldg(gn + i);
-        for (uint32_t i = threadIdx.x; i < n_geom4; i += blockDim.x) geom[i] = __ldg(gg + i);
-        for (uint32_t i = threadIdx.x; i < n_mat4; i += blockDim.x) mats[i] = __ldg(gm + i);
-        for (uint32_t i = threadIdx.x; i < n_tex4; i += blockDim.x) tex[i] = __ldg(gt + i);
-        *stack = reinterpret_cast<int*>(tex + n_tex4);
-        __syncthreads();
-        SmemAcc a; a.nodes = nodes; a.geom = geom; a.mats = mats; a.tex = tex;
-        return a;
-    }
-};
-template <> struct Stager<GmemAcc> {
-    static __device__ __forceinline__ GmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
-        uint32_t n_top4 = plan.n_top * 4;
-        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
-        for (uint32_t i = threadIdx.x; i < n_top4; i += blockDim.x) smem[i] = __ldg(gn + i);
-        *stack = reinterpret_cast<int*>(smem + n_top4);
-        __syncthreads();
-        GmemAcc a;
-        a.nodes = gn; a.geom = reinterpret_cast<const float4*>(s.geom);
-        a.mats = reinterpret_cast<const float4*>(s.mats); a.tex = reinterpret_cast<const float4*>(s.tex);
-        a.top = smem; a.n_top = (int)plan.n_top;
-        return a;
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// K2: persistent path-tracing megakernel.
-// Grid = (#SMs x resident CTAs); each warp pulls 8x4-pixel tiles from a global counter
-// (bottom rows first: the geometry-heavy tiles are scheduled before the cheap sky tiles).
-// One lane owns one pixel and walks its samples in order with path regeneration: a lane
-// whose path ends starts its next sample at the top of the loop instead of idling until
-// the warp's longest path finishes, so every traversal round has as many live lanes as the
-// tile still has work for.  Per-pixel sums stay in registers and are written once
-// (render.rs:59,66,68), as float4 {r, g, b, n}.
-// ------------------------------------------------------------------------------------------
-template <class Acc, bool COUNT>
-__global__ void __launch_bounds__(BLOCK) path_trace_kernel(const __grid_constant__ RenderArgs a) {
-    extern __shared__ float4 smem[];
-    int* stack_base;
-    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
-    int* stack = stack_base + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const TopPrims top = top_of(a.scene);
-
-    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
-
-    for (;;) {
-        unsigned int j = 0;
-        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
-        j = __shfl_sync(FULL, j, 0);
-        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
-        if (t64 >= a.n_tiles) break;
-        uint32_t t = (uint32_t)t64;
-        uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-        uint32_t px = tx * TILE_W + (lane & (TILE_W - 1));
-        uint32_t py = (a.tile_row0 + ty) * TILE_H + (lane >> 3);
-        bool valid = px < a.cam.width && py >= a.row_begin && py < a.row_end;
-        uint32_t pix = py * a.cam.width + px;
-
-        float3 sum = f3(0.f, 0.f, 0.f);
-        uint32_t s = 0, nrays = 0, nexh = 0;
-        TravCounters tc; tc.nodes = 0; tc.prims = 0;
-        bool alive = false;
-        Rng rng; rng.state = 0; rng.inc = 1;
-        RayF ray = make_ray(f3(0, 0, 0), f3(0, 0, 1));
-        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
-        uint32_t depth = 0;
-
-        for (;;) {
-            if (!alive && valid && s < a.samples) {
-                // render_scanline body, render.rs:60-66
-                rng.init(a.keys, pix, a.sample_offset + s);
-                float jx = (float)px + rng.gen();
-                float jy = (float)py + rng.gen();
-                float3 o, d;
-                pixel_ray(a.cam, rng, jx, jy, &o, &d);
-                ray = make_ray(o, d);
-                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
-                depth = a.max_depth;
-                alive = depth > 0;
-                ++s;
-            }
-            if (!__any_sync(FULL, alive)) break;
-            if (alive) {
-                // one iteration of ray_color's loop, render.rs:30-46
-                Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
-                closest_hit<COUNT>(ray, acc, top, stack, BLOCK, 0.001f, c, tc);
-                ++nrays;
-                bool done;
-                if (c.code < 0) {
-                    emit = emit + atten * background(a.scene, ray.d);
-                    done = true;
-                } else {
-                    HitRec h = make_hit(ray, acc, c);
-                    ShadeOut so = shade(a.scene, acc, ray, h, rng, atten, emit);
-                    done = !so.scattered;
-                    if (!done) {
-                        ray = make_ray(so.o, so.d);
-                        if (--depth == 0) { done = true; ++nexh; }
-                    }
-                }
-                if (done) { sum = sum + emit; alive = false; }
-            }
-        }
-        if (valid) {
-            float4* dst = a.accum + pix;
-            float4 v = make_float4(sum.x, sum.y, sum.z, (float)a.samples);
-            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
-        }
-        w_rays += nrays; w_exh += nexh; w_paths += valid ? a.samples : 0;
-        if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
-    }
-    // one set of atomics per warp per kernel
-    for (int o = 16; o > 0; o >>= 1) {
-        w_rays += __shfl_down_sync(FULL, w_rays, o);
-        w_paths += __shfl_down_sync(FULL, w_paths, o);
-        w_exh += __shfl_down_sync(FULL, w_exh, o);
-        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters->rays, w_rays);
-        atomicAdd(&a.counters->paths, w_paths);
-        atomicAdd(&a.counters->exhausted, w_exh);
-        if (COUNT) { atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims); }
-    }
-}
-
-constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + stream, tile pixel
-
-// Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
-// result does not depend on which lane traced which sample, nor on scheduling or sharding.
-__device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v) {
-    // 2^-32 fixed point; non-finite contributions are dropped (a NaN sample would blacken the
-    // reference's pixel; here it contributes nothing)
-    const float S = 4294967296.0f;
-    if (fabsf(v.x + v.y + v.z) <= 3.0e38f) {   // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative)
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2 (v2): the same persistent kernel restructured for SIMT efficiency (ncu on v1: 8.1 of 32
-// lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble
-// texture at 2.7):
-//  * while-while traversal: every lane runs inner-node visits until it holds a leaf, then the
-//    warp tests the postponed leaves together;
-//  * the traversal cursor is resumable, and the warp leaves the traversal loop as soon as
-//    fewer than `trav_threshold` lanes are still traversing: finished lanes shade, scatter and
-//    start their next segment (or next sample) instead of idling until the slowest lane ends;
-//  * scene-spanning primitives are tested up front, uniformly (DeviceScene::top_prims);
-//  * the Perlin marble is evaluated by the whole warp (coop_turbulence);
-//  * one-FMA slab planes against padded boxes (FAST).
-// ------------------------------------------------------------------------------------------
-template <class Acc, bool COUNT, bool FAST, int BLK, int MINB>
-__global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_constant__ RenderArgs a) {
-    extern __shared__ float4 smem[];
-    int* stack_base;
-    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
-    int* stack = stack_base + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt = (1u << lane) - 1u;
-    // per-warp fixed-point accumulators [32 pixels][3] behind the stack columns
-    long long* wacc = reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (threadIdx.x >> 5) * 96;
-    // per-warp queue of generated primary rays, SoA [RAYQ_FIELDS][RAYQ_SLOTS] behind the accumulators
-    uint32_t* rayq = reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
-                     + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
-    const float T_MIN = 0.001f;                      // render.rs:31
-    const bool has_perlin = a.scene.perlin != nullptr;
-
-    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
-    // lane-utilisation diagnostics (COUNT only, lane 0 of each warp):
-    //  d0 outer iterations, d1 sum of alive lanes, d2 sum of lanes with no samples left,
-    //  d3 traversal rounds, d4 sum of traversing lanes per round, d5 sum of lanes shaded,
-    //  d6 sum of lanes regenerated, d7 inner-node visit steps (warp-level)
-    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
-
-    for (;;) {
-        unsigned int j = 0;
-        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
-        j = __shfl_sync(FULL, j, 0);
-        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
-        if (t64 >= a.n_tiles) break;
-        uint32_t t = (uint32_t)t64;
-        uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-        const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
-        const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
-        const bool valid = my_px < a.cam.width && my_py >= a.row_begin && my_py < a.row_end;
-        // The tile's work list: item i = sample * nv + k (k-th valid pixel).  Any lane takes the
-        // next item when its path ends, so all lanes stay busy until the tile is finished
-        // (with lane = pixel, 17 % of the lanes sat out of samples at tile ends).
-        const unsigned valid_mask = __ballot_sync(FULL, valid);
-        const uint32_t nv = (uint32_t)__popc(valid_mask);
-        const uint32_t n_items = a.samples * nv;
-        uint32_t next_item = 0;          // next work-list item to generate
-        uint32_t q_head = 0, q_count = 0;  // the warp's ring of generated primary rays
-        for (int k = lane; k < 96; k += 32) wacc[k] = 0;
-        __syncwarp();
-        uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
-        uint32_t nrays = 0, nexh = 0;   // nrays: warp total (same value in every lane), nexh: per lane
-        TravCounters tc; tc.nodes = 0; tc.prims = 0;
-        bool alive = false;
-        Rng rng; rng.state = 0; rng.inc = 1;
-        RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
-        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
-        uint32_t depth = 0;
-        int node = B200RT_TRAV_DONE;
-        const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
-        uint32_t top_sp = stack_s + BLK * 4;   // shared-window address of the next free slot of this lane's stack column
-        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
-        stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
-
-        // One outer iteration = shade the lanes whose traversal finished, hand new paths to the
-        // lanes without one, set up the new segments of BOTH groups together (one copy of the ray
-        // set-up + up-front primitive code, run at ~30 lanes instead of twice at 6 and 18), traverse.
-        for (;;) {
-            // ---- shade: ray_color's loop body, render.rs:31-46 ----
-            bool fin = alive && node == B200RT_TRAV_DONE;
-            if (COUNT) { d0 += 1; d5 += __popc(__ballot_sync(FULL, fin)); }
-            bool hit = fin && c.code >= 0;
-            bool done = false, setup = false;
-            HitRec h;
-            ShadePrep sp_;
-            sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
-            h.p = f3(0.f, 0.f, 0.f);
-            if (fin && !hit) {
-                emit = emit + atten * background(a.scene, ray.d);
-                done = true;
-            }
-            if (hit) {
-                h = make_hit(ray, acc, c);
-                sp_ = shade_prepare(a.scene, acc, h);
-            }
-            float turb = 0.0f;
-            if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))   // warp-uniform: skip the call when no lane asks
-                turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
-            if (hit) {
-                float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
-                ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
-                done = !so.scattered;
-                if (!done) {
-                    if (--depth == 0) { done = true; ++nexh; }
-                    else { ray.o = so.o; ray.d = so.d; setup = true; }
-                }
-            }
-            if (done) { acc_add(wacc, pl, emit); alive = false; }
-
-            // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
-            // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG
-            // keying, jitter, lens rejection loop, Camera::pixel_ray) and handed out to the ~6 lanes
-            // per iteration whose path ended; generating them on demand ran that code at 6 lanes.
-            unsigned want_m = __ballot_sync(FULL, !alive);
-            const uint32_t want = (uint32_t)__popc(want_m);
-            if (q_count < want && next_item < n_items) {           // warp-uniform
-                __syncwarp();
-                // top the ring up to 32 entries: the first (32 - q_count) lanes generate
-                const uint32_t n_new = min(RAYQ_SLOTS - q_count, n_items - next_item);
-                uint32_t item = next_item + (uint32_t)lane;
-                if ((uint32_t)lane < n_new) {
-                    uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
-                    uint32_t kth = item - sidx * nv;
-                    uint32_t qpl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
-                    uint32_t px = px0 + (qpl & (TILE_W - 1)), py = py0 + (qpl >> 3);
-                    Rng qr;
-                    qr.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
-                    float jx = (float)px + qr.gen();
-                    float jy = (float)py + qr.gen();
-                    float3 qo, qd;
-                    pixel_ray(a.cam, qr, jx, jy, &qo, &qd);
-                    uint32_t slot = (q_head + q_count + (uint32_t)lane) & (RAYQ_SLOTS - 1);
-                    rayq[0 * RAYQ_SLOTS + slot] = __float_as_uint(qo.x); rayq[1 * RAYQ_SLOTS + slot] = __float_as_uint(qo.y);
-                    rayq[2 * RAYQ_SLOTS + slot] = __float_as_uint(qo.z); rayq[3 * RAYQ_SLOTS + slot] = __float_as_uint(qd.x);
-                    rayq[4 * RAYQ_SLOTS + slot] = __float_as_uint(qd.y); rayq[5 * RAYQ_SLOTS + slot] = __float_as_uint(qd.z);
-                    rayq[6 * RAYQ_SLOTS + slot] = qr.state; rayq[7 * RAYQ_SLOTS + slot] = qr.inc; rayq[8 * RAYQ_SLOTS + slot] = qpl;
-                }
-                next_item += n_new; q_count += n_new;
-                __syncwarp();
-            }
-            const uint32_t rank = (uint32_t)__popc(want_m & lt);
-            bool regen = !alive && rank < q_count;
-            if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
-            if (regen) {
-                uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);
-                ray.o = f3(__uint_as_float(rayq[0 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[1 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[2 * RAYQ_SLOTS + slot]));
-                ray.d = f3(__uint_as_float(rayq[3 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[4 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[5 * RAYQ_SLOTS + slot]));
-                rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot]; pl = rayq[8 * RAYQ_SLOTS + slot];
-                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
-                depth = a.max_depth;
-                alive = depth > 0;
-                setup = alive;
-            }
-            {
-                uint32_t taken = min(want, q_count);
-                q_head = (q_head + taken) & (RAYQ_SLOTS - 1); q_count -= taken;
-            }
-            if (!__any_sync(FULL, alive)) break;
-            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
-
-            // ---- new segment: per-ray constants, then the scene-spanning primitives ----
-            if (setup) {
-                // IEEE reciprocals, taken once: the up-front rect/box tests need exactly these
-                // (bit-reproducible on the CPU), and the slab tests take them too
-                float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
-                ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
-                ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
-                ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
-                c.t = INFINITY; c.code = -1; c.face = 0;
-                // the list is indexed in the kernel parameters (constant bank): a register copy indexed by a
-                // loop counter would live in local memory
-#pragma unroll 1
-                for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
-                    if (COUNT) tc.prims++;
-                    hit_leaf(ray, acc, a.scene.top_prims[k], T_MIN, c, &inv_e);
-                }
-                node = 0; top_sp = stack_s + BLK * 4;
-            }
-            nrays += (uint32_t)__popc(__ballot_sync(FULL, setup));   // warp-uniform count: no per-lane counter to keep live
-
-            // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
-            for (;;) {
-                if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
-                // (a warp-uniform inner loop that stops below a lane threshold, and a cap on the steps per
-                //  round, were measured: 15-18 lanes per step instead of 13.6, but no faster — profiles/README.md)
-                while (node >= 0 && node != B200RT_TRAV_DONE) {
-                    if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
-                    trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
-                }
-                if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
-                unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
-                if ((uint32_t)__popc(still) < a.trav_threshold) break;
-            }
-        }
-        __syncwarp();
-        if (valid) {
-            const float inv = 1.0f / 4294967296.0f;
-            float4* dst = a.accum + (my_py * a.cam.width + my_px);
-            float4 v = make_float4((float)wacc[lane * 3 + 0] * inv, (float)wacc[lane * 3 + 1] * inv, (float)wacc[lane * 3 + 2] * inv, (float)a.samples);
-            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
-        }
-        __syncwarp();
-        w_rays += lane == 0 ? nrays : 0u; w_exh += nexh; w_paths += lane == 0 ? n_items : 0u;   // every work-list item became one path
-        if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        w_rays += __shfl_down_sync(FULL, w_rays, o);
-        w_paths += __shfl_down_sync(FULL, w_paths, o);
-        w_exh += __shfl_down_sync(FULL, w_exh, o);
-        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters->rays, w_rays);
-        atomicAdd(&a.counters->paths, w_paths);
-        atomicAdd(&a.counters->exhausted, w_exh);
-        if (COUNT) { atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims); }
-    }
-    if (COUNT) {
-        // d7 was counted by whichever lane led each divergent step: sum it over the warp
-        for (int o = 16; o > 0; o >>= 1) d7 += __shfl_down_sync(FULL, d7, o);
-        if (lane == 0) {
-            atomicAdd(&a.counters->diag[0], d0); atomicAdd(&a.counters->diag[1], d1); atomicAdd(&a.counters->diag[2], d2); atomicAdd(&a.counters->diag[3], d3);
-            atomicAdd(&a.counters->diag[4], d4); atomicAdd(&a.counters->diag[5], d5); atomicAdd(&a.counters->diag[6], d6); atomicAdd(&a.counters->diag[7], d7);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K2 (v3): warp-level wavefront over a shared-memory path pool.
-//
-// Measured on v2 (scripts/diag.py): 26 lanes traverse per round but only 12.6 run each
-// inner-node step (lanes differ in how many nodes they visit), 17 % of the lanes sit out of
-// samples at the end of a tile, and shading batches hold ~21 lanes of mixed materials.  A
-// lane-owns-a-pixel design can only trade traversal efficiency against shading efficiency, so
-// here lanes are decoupled from paths:
-//   * every warp owns a pool of P path slots in shared memory (SoA: ray, attenuation, RNG,
-//     depth, hit) and the (pixel, sample) work list of its 8x4 tile;
-//   * GENERATE, TRAVERSE and SHADE run as warp-wide batches over slots picked with
-//     __ballot_sync/__popc compaction, so each phase runs on (up to) 32 live lanes;
-//   * in TRAVERSE a lane that finishes stores its hit and immediately claims the next waiting
-//     slot; when the queue is dry and only stragglers run, they are parked (cursor stays in
-//     registers) while the warp shades / generates, and resume afterwards;
-//   * per-pixel sums are 64-bit fixed point (2^-32) in shared memory: integer adds commute, so
-//     the image stays bit-deterministic and independent of scheduling and tile sharding.
-// ------------------------------------------------------------------------------------------
-// Slot states.  A finished traversal parks its slot under the shading KIND it needs, so
-// SHADE batches can be claimed one material at a time (no divergence inside a batch).
-enum { SLOT_EMPTY = 0, SLOT_TRAV = 1, SLOT_RUN = 2, SLOT_SHADE0 = 3 };
-enum { SK_MISS = 0, SK_METAL = 1, SK_DIELECTRIC = 2, SK_LAMBERT_SOLID = 3, SK_OTHER = 4, SK_COUNT = 5 };
-constexpr int POOL_FIELDS = 15;
-__host__ __device__ constexpr int pool_words(int P) { return 192 + 32 + POOL_FIELDS * P; }
-
-template <int P> struct Pool {
-    long long* acc;          // [32 pixels][3] fixed-point sums
-    int* list;               // [32] compaction scratch
-    float *ox, *oy, *oz, *dx, *dy, *dz, *ax, *ay, *az, *t;
-    int* code;
-    uint32_t *rs, *ri, *meta, *state;   // meta: pixel (5) | box face (3) << 5 | depth << 8
-    __device__ __forceinline__ explicit Pool(uint32_t* base) {
-        acc = reinterpret_cast<long long*>(base);
-        list = reinterpret_cast<int*>(base + 192);
-        float* f = reinterpret_cast<float*>(base + 224);
-        ox = f; oy = f + P; oz = f + 2 * P; dx = f + 3 * P; dy = f + 4 * P; dz = f + 5 * P;
-        ax = f + 6 * P; ay = f + 7 * P; az = f + 8 * P; t = f + 9 * P;
-        code = reinterpret_cast<int*>(f + 10 * P);
-        rs = reinterpret_cast<uint32_t*>(f + 11 * P); ri = rs + P; meta = rs + 2 * P; state = rs + 3 * P;
-    }
-};
-
-// Compaction: the lanes flagged `want` receive distinct slots currently in `state_wanted`,
-// lowest slot first; -1 when the pool has no more.  Returns how many such slots exist in *total.
-// Out of line (it is called from every phase) and scalar in/out only, so the call costs no
-// local-memory traffic: returns (slot & 0xffff) | (total << 16), slot 0xffff = none.
-template <int P>
-__device__ __noinline__ uint32_t claim_slots_packed(const uint32_t* state, int* list, uint32_t state_wanted, bool want) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < P / 32; ++k) {
-        bool is = state[k * 32 + lane] == state_wanted;
-        unsigned m = __ballot_sync(FULL, is);
-        int rank = n + __popc(m & lt);
-        if (is && rank < 32) list[rank] = k * 32 + lane;
-        n += __popc(m);
-    }
-    __syncwarp();
-    unsigned wm = __ballot_sync(FULL, want);
-    int j = __popc(wm & lt);
-    uint32_t slot = (want && j < n) ? (uint32_t)list[j] : 0xffffu;
-    __syncwarp();
-    return slot | ((uint32_t)n << 16);
-}
-template <int P>
-__device__ __forceinline__ int claim_slots(const Pool<P>& pool, uint32_t state_wanted, bool want, int lane, int* total) {
-    uint32_t r = claim_slots_packed<P>(pool.state, pool.list, state_wanted, want);
-    *total = (int)(r >> 16);
-    uint32_t slot = r & 0xffffu;
-    return slot == 0xffffu ? -1 : (int)slot;
-}
-
-// Store a freshly produced ray (camera ray or scattered ray) into its slot, after testing it
-// against the scene-spanning primitives: that test runs here, in a full uniform batch.
-template <bool COUNT, int P, class Acc>
-__device__ __forceinline__ void produce_ray(const Pool<P>& pool, int slot, const Acc& acc, const TopPrims& top, float3 o, float3 d, float3 atten,
-                                            const Rng& rng, uint32_t pixel, uint32_t depth, TravCounters& tc) {
-    RayF r = make_ray_shade(o, d);
-    Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
-    hit_top_prims<COUNT>(r, acc, top, 0.001f, c, tc);
-    pool.ox[slot] = o.x; pool.oy[slot] = o.y; pool.oz[slot] = o.z;
-    pool.dx[slot] = d.x; pool.dy[slot] = d.y; pool.dz[slot] = d.z;
-    pool.ax[slot] = atten.x; pool.ay[slot] = atten.y; pool.az[slot] = atten.z;
-    pool.rs[slot] = rng.state; pool.ri[slot] = rng.inc;
-    pool.t[slot] = c.t; pool.code[slot] = c.code;
-    pool.meta[slot] = pixel | ((uint32_t)c.face << 5) | (depth << 8);
-    pool.state[slot] = SLOT_TRAV;
-}
-
-template <class Acc, bool COUNT, bool FAST, int BLK, int P>
-__global__ void __launch_bounds__(BLK, 1) path_trace_kernel_v3(const __grid_constant__ RenderArgs a) {
-    extern __shared__ float4 smem[];
-    int* stack_base;
-    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
-    int* stack = stack_base + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt = (1u << lane) - 1u;
-    Pool<P> pool(reinterpret_cast<uint32_t*>(stack_base + a.plan.stack_depth * BLK) + warp * pool_words(P));
-    const TopPrims top = top_of(a.scene);
-    const float T_MIN = 0.001f;                      // render.rs:31
-    const bool has_perlin = a.scene.perlin != nullptr;
-    const int T_INNER = (int)a.wf_inner, F_FETCH = (int)a.wf_fetch, T_PARK = (int)a.wf_park;
-
-    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
-    // diagnostics (COUNT): d0 policy iterations, d1 shade batches, d2 kinds per shade batch,
-    // d3 inner warp-steps, d4 lanes in inner steps, d5 lanes shaded, d6 lanes generated, d7 fetch batches
-    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
-    TravCounters tc; tc.nodes = 0; tc.prims = 0;
-
-    for (;;) {
-        unsigned int j = 0;
-        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
-        j = __shfl_sync(FULL, j, 0);
-        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
-        if (t64 >= a.n_tiles) break;
-        uint32_t tile = (uint32_t)t64;
-        uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-        const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
-        // this lane's own pixel (validity and the final write); slots carry arbitrary pixels
-        const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
-        const bool my_valid = my_px < a.cam.width && my_py >= a.row_begin && my_py < a.row_end;
-        const unsigned valid_mask = __ballot_sync(FULL, my_valid);
-
-        // reset the pool
-#pragma unroll
-        for (int k = 0; k < P / 32; ++k) pool.state[k * 32 + lane] = SLOT_EMPTY;
-        for (int k = lane; k < 96; k += 32) pool.acc[k] = 0;
-        __syncwarp();
-
-        // work list: item i = sample * nv + k, k-th valid pixel of the tile (nv = 32 for full tiles)
-        const uint32_t nv = (uint32_t)__popc(valid_mask);
-        uint32_t next_item = 0;
-        const uint32_t n_items = (a.max_depth == 0) ? 0u : a.samples * nv;
-
-        // warp-uniform slot census, maintained incrementally
-        int nE = P, nT = 0, nS = 0;
-        // per-lane traversal context (may stay parked across shade / generate phases)
-        bool running = false;
-        int cur = -1, node = B200RT_TRAV_DONE, sp = 0;
-        RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
-        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
-        uint32_t nrays = 0, nexh = 0, npaths = 0;
-
-        for (;;) {
-            __syncwarp();
-            const int nRun = __popc(__ballot_sync(FULL, running));
-            const bool can_gen = next_item < n_items && nE > 0;
-            const bool full_gen = next_item < n_items && nE >= 32;
-            if (COUNT) d0 += 1;
-
-            int phase;   // 0 shade, 1 generate, 2 traverse
-            if (nS >= 32) phase = 0;
-            else if (full_gen) phase = 1;
-            else if (nT > 0 || nRun >= T_PARK || (nRun > 0 && nS == 0 && !can_gen)) phase = 2;
-            else if (nS > 0) phase = 0;
-            else if (can_gen) phase = 1;
-            else if (nRun > 0) phase = 2;
-            else break;
-
-            // a ray produced by GENERATE or by SHADE's scatter; stored by the one produce_ray below
-            bool produced = false;
-            int p_slot = -1; uint32_t p_pixel = 0, p_depth = 0;
-            float3 p_o = f3(0, 0, 0), p_d = f3(0, 0, 1), p_atten = f3(1, 1, 1);
-            Rng p_rng; p_rng.state = 0; p_rng.inc = 1;
-
-            if (phase == 1) {
-                // ---- GENERATE: render_scanline's sample loop body, render.rs:60-66 ----
-                int total;
-                int slot = claim_slots<P>(pool, SLOT_EMPTY, true, lane, &total);
-                unsigned gm = __ballot_sync(FULL, slot >= 0);
-                uint32_t take = min((uint32_t)__popc(gm), n_items - next_item);
-                uint32_t my_rank = (uint32_t)__popc(gm & lt);
-                bool have = slot >= 0 && my_rank < take;
-                uint32_t item = next_item + my_rank;
-                next_item += take;
-                if (have) {
-                    uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
-                    uint32_t kth = item - sidx * nv;
-                    uint32_t pl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
-                    uint32_t px = px0 + (pl & (TILE_W - 1)), py = py0 + (pl >> 3);
-                    Rng rng; rng.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
-                    float jx = (float)px + rng.gen();
-                    float jy = (float)py + rng.gen();
-                    float3 o, d;
-                    pixel_ray(a.cam, rng, jx, jy, &o, &d);
-                    produced = true; p_slot = slot; p_o = o; p_d = d; p_rng = rng; p_pixel = pl; p_depth = a.max_depth;
-                    ++npaths;
-                }
-                nE -= (int)take; nT += (int)take;
-                if (COUNT) d6 += take;
-            } else if (phase == 2) {
-                // ---- TRAVERSE: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
-                bool do_fetch = true;
-                for (;;) {
-                    // fetch: idle lanes claim waiting slots; the scene-spanning primitives were
-                    // already tested by the producer, so a fetch is 9 loads and 3 reciprocals
-                    if (do_fetch && nT > 0 && __any_sync(FULL, !running)) {
-                        int total;
-                        int slot = claim_slots<P>(pool, SLOT_TRAV, !running, lane, &total);
-                        if (slot >= 0) {
-                            pool.state[slot] = SLOT_RUN;
-                            float3 o = f3(pool.ox[slot], pool.oy[slot], pool.oz[slot]), d = f3(pool.dx[slot], pool.dy[slot], pool.dz[slot]);
-                            ray = FAST ? make_ray_fast(o, d) : make_ray(o, d);
-                            c.t = pool.t[slot]; c.code = pool.code[slot]; c.face = (int)((pool.meta[slot] >> 5) & 7u);
-                            node = 0; sp = 0; cur = slot; running = true;
-                        }
-                        nT -= __popc(__ballot_sync(FULL, slot >= 0));
-                        if (COUNT) d7 += 1;
-                    }
-                    // inner-node steps while enough lanes want one (always at least one step)
-                    bool in = running && node >= 0 && node != B200RT_TRAV_DONE;
-                    if (__any_sync(FULL, in)) {
-                        do {
-                            if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, in)); }
-                            if (in) trav_inner<COUNT, FAST>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
-                            in = running && node >= 0 && node != B200RT_TRAV_DONE;
-                        } while (__popc(__ballot_sync(FULL, in)) >= T_INNER);
-                    }
-                    // postponed leaves
-                    if (running && node < 0) trav_leaf<COUNT>(ray, acc, stack, BLK, T_MIN, c, node, sp, tc);
-                    // finished traversals: park the slot under its shading kind, release the lane
-                    bool fin = running && node == B200RT_TRAV_DONE;
-                    if (fin) {
-                        uint32_t kind = SK_MISS;
-                        if (c.code >= 0) {
-                            MatRec m = acc.mat((int)((uint32_t)c.code & B200RT_LEAF_ID_MASK));
-                            kind = m.kind == B200RT_MAT_METAL ? SK_METAL : (m.kind == B200RT_MAT_DIELECTRIC ? SK_DIELECTRIC
-                                   : ((m.kind == B200RT_MAT_LAMBERTIAN && m.tex < 0) ? SK_LAMBERT_SOLID : SK_OTHER));
-                        }
-                        pool.t[cur] = c.t; pool.code[cur] = c.code;
-                        pool.meta[cur] = (pool.meta[cur] & ~(7u << 5)) | ((uint32_t)c.face << 5);
-                        pool.state[cur] = SLOT_SHADE0 + kind;
-                        running = false; cur = -1;
-                    }
-                    nS += __popc(__ballot_sync(FULL, fin));
-                    int n_run = __popc(__ballot_sync(FULL, running));
-                    if (nT > 0) do_fetch = (32 - n_run >= F_FETCH) || n_run == 0;   // refill when enough lanes idle
-                    else {
-                        do_fetch = false;
-                        if (n_run == 0) break;
-                        // park the stragglers when a full batch of other work is ready
-                        if (n_run < T_PARK && (nS >= 32 || (next_item < n_items && nE >= 32))) break;
-                    }
-                }
-                continue;
-            } else {
-                // ---- SHADE: ray_color's loop body, render.rs:31-46, one or two kinds per batch ----
-                int cnt[SK_COUNT];
-#pragma unroll
-                for (int q = 0; q < SK_COUNT; ++q) cnt[q] = 0;
-#pragma unroll
-                for (int k = 0; k < P / 32; ++k) {
-                    uint32_t st = pool.state[k * 32 + lane];
-#pragma unroll
-                    for (int q = 0; q < SK_COUNT; ++q) cnt[q] += __popc(__ballot_sync(FULL, st == (uint32_t)(SLOT_SHADE0 + q)));
-                }
-                int k1 = 0;
-#pragma unroll
-                for (int q = 1; q < SK_COUNT; ++q) if (cnt[q] > cnt[k1]) k1 = q;
-                int total;
-                int slot = claim_slots<P>(pool, SLOT_SHADE0 + k1, true, lane, &total);
-                if (COUNT) { d1 += 1; d2 += 1; }
-                if (total < 32) {
-                    int k2 = -1;
-#pragma unroll
-                    for (int q = 0; q < SK_COUNT; ++q) if (q != k1 && cnt[q] > 0 && (k2 < 0 || cnt[q] > cnt[k2])) k2 = q;
-                    if (k2 >= 0) {
-                        int total2;
-                        int slot2 = claim_slots<P>(pool, SLOT_SHADE0 + k2, slot < 0, lane, &total2);
-                        if (slot < 0) slot = slot2;
-                        if (COUNT) d2 += 1;
-                    }
-                }
-                bool have = slot >= 0;
-                int n_have = __popc(__ballot_sync(FULL, have));
-                if (COUNT) d5 += n_have;
-                bool hit = false;
-                HitRec h; h.p = f3(0.f, 0.f, 0.f);
-                ShadePrep sp_; sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
-                RayF r = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
-                float3 atten = f3(1, 1, 1);
-                uint32_t meta = 0;
-                bool cont = false;
-                if (have) {
-                    r = make_ray_shade(f3(pool.ox[slot], pool.oy[slot], pool.oz[slot]), f3(pool.dx[slot], pool.dy[slot], pool.dz[slot]));
-                    atten = f3(pool.ax[slot], pool.ay[slot], pool.az[slot]);
-                    meta = pool.meta[slot];
-                    Closest hc; hc.t = pool.t[slot]; hc.code = pool.code[slot]; hc.face = (int)((meta >> 5) & 7u);
-                    hit = hc.code >= 0;
-                    if (!hit) {
-                        acc_add(pool.acc, meta & 31u, atten * background(a.scene, r.d));
-                    } else {
-                        h = make_hit(r, acc, hc);
-                        sp_ = shade_prepare(a.scene, acc, h);
-                    }
-                }
-                float turb = 0.0f;
-                if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))
-                    turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
-                if (hit) {
-                    Rng rng; rng.state = pool.rs[slot]; rng.inc = pool.ri[slot];
-                    float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
-                    float3 emit = f3(0.f, 0.f, 0.f);
-                    ShadeOut so = shade_finish(r, h, sp_.m, albedo, rng, atten, emit);
-                    if (emit.x != 0.f || emit.y != 0.f || emit.z != 0.f) acc_add(pool.acc, meta & 31u, emit);
-                    uint32_t depth = meta >> 8;
-                    cont = so.scattered;
-                    if (cont) { --depth; if (depth == 0) { cont = false; ++nexh; } }
-                    if (cont) { produced = true; p_slot = slot; p_o = so.o; p_d = so.d; p_atten = atten; p_rng = rng; p_pixel = meta & 31u; p_depth = depth; }
-                }
-                if (have && !cont) pool.state[slot] = SLOT_EMPTY;
-                int n_cont = __popc(__ballot_sync(FULL, cont));
-                nS -= n_have; nT += n_cont; nE += n_have - n_cont;
-            }
-            // the new rays meet the scene-spanning primitives here, in one full uniform batch
-            if (produced) { produce_ray<COUNT, P>(pool, p_slot, acc, top, p_o, p_d, p_atten, p_rng, p_pixel, p_depth, tc); ++nrays; }
-        }
-        __syncwarp();
-        if (my_valid) {
-            const float inv = 1.0f / 4294967296.0f;
-            float4 v = make_float4((float)pool.acc[lane * 3 + 0] * inv, (float)pool.acc[lane * 3 + 1] * inv, (float)pool.acc[lane * 3 + 2] * inv, (float)a.samples);
-            float4* dst = a.accum + (my_py * a.cam.width + my_px);
-            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
-        }
-        w_rays += nrays; w_exh += nexh; w_paths += npaths;
-    }
-    if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
-    for (int o = 16; o > 0; o >>= 1) {
-        w_rays += __shfl_down_sync(FULL, w_rays, o);
-        w_paths += __shfl_down_sync(FULL, w_paths, o);
-        w_exh += __shfl_down_sync(FULL, w_exh, o);
-        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
-    }
-    if (lane == 0) {
-        atomicAdd(&a.counters->rays, w_rays);
-        atomicAdd(&a.counters->paths, w_paths);
-        atomicAdd(&a.counters->exhausted, w_exh);
-        if (COUNT) {
-            atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims);
-            atomicAdd(&a.counters->diag[0], d0); atomicAdd(&a.counters->diag[1], d1); atomicAdd(&a.counters->diag[2], d2); atomicAdd(&a.counters->diag[3], d3);
-            atomicAdd(&a.counters->diag[4], d4); atomicAdd(&a.counters->diag[5], d5); atomicAdd(&a.counters->diag[6], d6); atomicAdd(&a.counters->diag[7], d7);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K1: closest-hit over a ray array, one thread per ray (grid-stride).
-// ------------------------------------------------------------------------------------------
-struct HitArgs {
-    DeviceScene scene; SmemPlan plan;
-    const B200rtRay* rays; size_t n; float t_min, t_max;
-    int32_t* ids; B200rtHit* hits; Counters* counters;
-};
-
-// K1 runs the SAME traversal code as the render kernel (per-segment set-up with shared IEEE reciprocals, up-front
-// primitives, trav_inner_s / trav_leaf_s over the sentinel stack; FAST = centre/half-extent boxes) so that the
-// bit-exact id / t / normal parity tests exercise the product's traversal, not a parity-only twin.
-template <class Acc, bool COUNT, bool FAST>
-__global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constant__ HitArgs a) {
-    extern __shared__ float4 smem[];
-    int* stack_base;
-    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
-    int* stack = stack_base + threadIdx.x;
-    stack[0] = B200RT_TRAV_DONE;
-    const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
-    TravCounters tc; tc.nodes = 0; tc.prims = 0;
-    unsigned long long nr = 0;
-    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BLOCK) {
-        B200rtRay in = a.rays[i];
-        RayF ray;
-        ray.o = f3(in.ox, in.oy, in.oz); ray.d = f3(in.dx, in.dy, in.dz);
-        float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
-        ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
-        ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
-        ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
-        Closest c; c.t = a.t_max; c.code = -1; c.face = 0;
-#pragma unroll 1
-        for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
-            if (COUNT) tc.prims++;
-            hit_leaf(ray, acc, a.scene.top_prims[k], a.t_min, c, &inv_e);
-        }
-        int node = 0;
-        uint32_t top_sp = stack_s + BLOCK * 4;
-        while (node != B200RT_TRAV_DONE) {
-            while (node >= 0 && node != B200RT_TRAV_DONE) trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
-            if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
-        }
-        ++nr;
-        int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_LEAF_ID_MASK);
-        a.ids[i] = id;
-        if (a.hits) {
-            B200rtHit out;
-            memset(&out, 0, sizeof out);
-            out.id = id;
-            if (id >= 0) {
-                HitRec h = make_hit(ray, acc, c);
-                float u, v;
-                hit_uv(h, acc, &u, &v);
-                out.t = h.t; out.p[0] = h.p.x; out.p[1] = h.p.y; out.p[2] = h.p.z;
-                out.n[0] = h.n.x; out.n[1] = h.n.y; out.n[2] = h.n.z;
-                out.u = u; out.v = v; out.front_face = h.front ? 1 : 0;
-            }
-            a.hits[i] = out;
-        }
-    }
-    if (a.counters) {
-        atomicAdd(&a.counters->rays, nr);
-        if (COUNT) { atomicAdd(&a.counters->nodes, (unsigned long long)tc.nodes); atomicAdd(&a.counters->prims, (unsigned long long)tc.prims); }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: resolve.  to_image (image.rs:34-40): c * (1/samples), sqrt, (x * 255.999) as u8
-// (saturating, NaN -> 0), vertical flip.  Evaluated in f64 like the reference so the bytes
-// are bit-identical to the oracle's for the same accumulation buffer.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned char to_pixel(double x) {
-    double v = x * 255.999;
-    if (!(v > 0.0)) return 0;
-    if (v >= 255.0) return 255;
-    return (unsigned char)v;
-}
-__global__ void resolve_kernel(const float4* __restrict__ accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* __restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t j = blockIdx.y;
-    if (i >= W || j >= H) return;
-    float4 c = accum[(size_t)j * W + i];
-    double n = samples ? (double)samples : (double)c.w;
-    double inv = 1.0 / n;
-    uint8_t* px = out + ((size_t)(H - 1 - j) * W + i) * 3;
-    px[0] = to_pixel(sqrt((double)c.x * inv));
-    px[1] = to_pixel(sqrt((double)c.y * inv));
-    px[2] = to_pixel(sqrt((double)c.z * inv));
-}
-
-
-// K3p: the cross-GPU sum fused into the resolve.  With sample-range sharding
-// every GPU holds a full-frame float4 buffer of its own samples; instead of an NCCL reduce onto
-// one GPU followed by resolve_kernel there, each GPU takes a band of rows, reads that band from
-// EVERY GPU's buffer through NVLink peer pointers (coalesced 16-byte loads), adds them in rank
-// order (so the bytes do not depend on timing), applies to_image's arithmetic and stores the
-// RGB8 band — through a peer pointer again — into the frame on the root GPU.  One pass, no
-// intermediate reduced buffer, and the traffic is spread over all GPUs' links.
-constexpr int MAX_PEERS = 16;
-struct PeerResolveArgs {
-    const float4* accum[MAX_PEERS];
-    uint32_t n_peers, W, H, samples, row_begin, row_end;
-    uint8_t* out;
-};
-__device__ __forceinline__ float4 peer_sum(const PeerResolveArgs& a, size_t idx) {
-    float4 c = __ldcg(a.accum[0] + idx);        // .cg: peer data must not be served from a stale L1 line
-    for (uint32_t r = 1; r < a.n_peers; ++r) {
-        float4 v = __ldcg(a.accum[r] + idx);
-        c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
-    }
-    return c;
-}
-__global__ void resolve_peers_kernel(const __grid_constant__ PeerResolveArgs a) {
-    const uint32_t j = a.row_begin + blockIdx.y;
-    if (j >= a.row_end) return;
-    const uint32_t groups = (a.W + 3) / 4;
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= groups) return;
-    const uint32_t i0 = g * 4;
-    uint8_t bytes[12];
-    uint32_t n_px = min(4u, a.W - i0);
-    for (uint32_t k = 0; k < n_px; ++k) {
-        float4 c = peer_sum(a, (size_t)j * a.W + i0 + k);
-        double n = a.samples ? (double)a.samples : (double)c.w;
-        double inv = 1.0 / n;
-        bytes[3 * k + 0] = to_pixel(sqrt((double)c.x * inv));
-        bytes[3 * k + 1] = to_pixel(sqrt((double)c.y * inv));
-        bytes[3 * k + 2] = to_pixel(sqrt((double)c.z * inv));
-    }
-    uint8_t* px = a.out + ((size_t)(a.H - 1 - j) * a.W + i0) * 3;
-    if (n_px == 4 && ((uintptr_t)px & 3u) == 0) {
-        uint32_t* w = reinterpret_cast<uint32_t*>(px);
-        w[0] = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | ((uint32_t)bytes[3] << 24);
-        w[1] = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | ((uint32_t)bytes[7] << 24);
-        w[2] = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | ((uint32_t)bytes[11] << 24);
-    } else {
-        for (uint32_t k = 0; k < 3 * n_px; ++k) px[k] = bytes[k];
-    }
-}
-
-
-// Cross-GPU ordering for the fused resolve without a library collective: every rank owns a small flag
-// array in peer-visible memory, [slot][rank] epochs.  signal = "my stream has reached this point" written
-// into every peer's array (release, system scope); wait = spin until all peers' epochs arrived (acquire).
-// slot 0 = "my accumulation buffer is complete", slot 1 = "I am done reading your buffer".
-constexpr uint32_t PEER_FLAG_STRIDE = 16;
-struct PeerSignalArgs { uint32_t* flags[MAX_PEERS]; uint32_t n_peers, my_rank, slot, epoch; };
-__global__ void peer_signal_kernel(const __grid_constant__ PeerSignalArgs a) {
-    uint32_t p = threadIdx.x;
-    if (p >= a.n_peers) return;
-    __threadfence_system();
-    uint32_t* dst = a.flags[p] + a.slot * PEER_FLAG_STRIDE + a.my_rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(dst), "r"(a.epoch) : "memory");
-}
-__global__ void peer_wait_kernel(const uint32_t* my_flags, uint32_t n_peers, uint32_t slot, uint32_t epoch, unsigned long long timeout_ns, uint32_t* timed_out) {
-    uint32_t r = threadIdx.x;
-    if (r >= n_peers) return;
-    const uint32_t* src = my_flags + slot * PEER_FLAG_STRIDE + r;
-    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-        uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-        if ((int32_t)(v - epoch) >= 0) break;
-        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > timeout_ns) { atomicExch(timed_out, 1u + r); break; }   // a missing peer must not hang the GPU: report and go on
-        __nanosleep(200);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// parity-hook kernels
-// ------------------------------------------------------------------------------------------
-__global__ void aabb_hit_kernel(const float* __restrict__ boxes6, const B200rtRay* __restrict__ rays, size_t n, float t_min, float t_max, uint8_t* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    B200rtRay in = rays[i];
-    RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
-    const float* b = boxes6 + i * 6;
-    float e;
-    out[i] = aabb_hit2(ray, b[0], b[1], b[2], b[3], b[4], b[5], t_min, t_max, &e) ? 1 : 0;
-}
-
-struct ScatterArgs { DeviceScene scene; const B200rtRay* rays; const B200rtHit* hits; size_t n; RngKeys keys; B200rtScatter* out; };
-__global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
-    // The render kernel's own shading sequence: shade_prepare -> warp-cooperative Perlin -> shade_finish.
-    // No early return: coop_turbulence is a warp collective (the grid is rounded up to whole warps).
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = i < a.n;
-    GmemAcc acc;
-    acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
-    acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
-    acc.top = nullptr; acc.n_top = 0;
-    B200rtRay in{}; B200rtHit hi{}; hi.id = -1;
-    if (in_range) { in = a.rays[i]; hi = a.hits[i]; }
-    B200rtScatter out; memset(&out, 0, sizeof out);
-    const bool valid = in_range && hi.id >= 0 && (uint32_t)hi.id < a.scene.n_prims;
-    RayF ray = make_ray(f3(in.ox, in.oy, in.oz), f3(in.dx, in.dy, in.dz));
-    // rebuild the device hit record from the caller's record; u,v come from the geometry
-    HitRec h;
-    h.id = hi.id; h.t = hi.t; h.p = f3(hi.p[0], hi.p[1], hi.p[2]); h.n = f3(hi.n[0], hi.n[1], hi.n[2]);
-    h.front = hi.front_face != 0;
-    h.n_out = h.front ? h.n : -h.n;
-    h.type = 0xffu; h.face = 0;
-    h.has_uv = true; h.uv_u = hi.u; h.uv_v = hi.v;   // Texture::value(record.u, record.v, ..), lambertian.rs:34
-    ShadePrep sp; sp.tex.need_perlin = false; sp.tex.perlin_idx = 0; sp.tex.perlin_scale = 0.f; sp.tex.rgb = f3(0, 0, 0);
-    if (valid) sp = shade_prepare(a.scene, acc, h);
-    const bool need = valid && sp.tex.need_perlin;
-    float turb = 0.0f;
-    if (a.scene.perlin != nullptr && __any_sync(0xffffffffu, need)) turb = coop_turbulence(a.scene.perlin, need, h.p, sp.tex.perlin_idx);
-    if (valid) {
-        Rng rng; rng.init(a.keys, (uint32_t)i, 0u);
-        uint32_t s0 = rng.state;
-        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
-        float3 albedo = sp.tex.need_perlin ? marble(sp.tex.perlin_scale, h.p, turb) : sp.tex.rgb;
-        ShadeOut so = shade_finish(ray, h, sp.m, albedo, rng, atten, emit);
-        out.ray.ox = so.o.x; out.ray.oy = so.o.y; out.ray.oz = so.o.z;
-        out.ray.dx = so.d.x; out.ray.dy = so.d.y; out.ray.dz = so.d.z;
-        out.attenuation[0] = atten.x; out.attenuation[1] = atten.y; out.attenuation[2] = atten.z;
-        out.emitted[0] = emit.x; out.emitted[1] = emit.y; out.emitted[2] = emit.z;
-        out.scattered = so.scattered ? 1 : 0;
-        // draws consumed = LCG steps between s0 and rng.state: recount by stepping
-        uint32_t st = s0, k = 0;
-        while (st != rng.state && k < 4096) { st = st * 747796405u + rng.inc; ++k; }
-        out.draws = k;
-    }
-    if (in_range) a.out[i] = out;
-}
-
-__global__ void camera_rays_kernel(DeviceCamera cam, const float* __restrict__ xy, size_t n, RngKeys keys, B200rtRay* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Rng rng; rng.init(keys, (uint32_t)i, 0u);
-    float3 o, d;
-    pixel_ray(cam, rng, xy[2 * i], xy[2 * i + 1], &o, &d);
-    B200rtRay r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-    out[i] = r;
-}
-
-struct TexArgs { DeviceScene scene; int32_t tex; const float* uvp5; size_t n; float* out; };
-__global__ void texture_value_kernel(const __grid_constant__ TexArgs a) {
-    // Texture::value the way the render kernel evaluates it: descent per lane, marble turbulence by the whole warp.
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = i < a.n;
-    GmemAcc acc;
-    acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
-    acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
-    acc.top = nullptr; acc.n_top = 0;
-    const float* q = a.uvp5 + (in_range ? i : 0) * 5;
-    HitRec h;
-    h.id = -1; h.type = 0xffu; h.face = 0; h.t = 0; h.front = true;
-    h.p = f3(q[2], q[3], q[4]); h.n = f3(0, 1, 0); h.n_out = h.n;
-    h.has_uv = true; h.uv_u = q[0]; h.uv_v = q[1];
-    TexResult r; r.need_perlin = false; r.perlin_idx = 0; r.perlin_scale = 0.f; r.rgb = f3(0, 0, 0);
-    if (in_range) r = texture_descend(acc, a.scene.images, a.tex, h);
-    const bool need = in_range && r.need_perlin;
-    float turb = 0.0f;
-    if (a.scene.perlin != nullptr && __any_sync(0xffffffffu, need)) turb = coop_turbulence(a.scene.perlin, need, h.p, r.perlin_idx);
-    float3 c = r.need_perlin ? marble(r.perlin_scale, h.p, turb) : r.rgb;
-    if (in_range) { a.out[i * 3 + 0] = c.x; a.out[i * 3 + 1] = c.y; a.out[i * 3 + 2] = c.z; }
-}
-
-__global__ void rng_kernel(RngKeys keys, uint32_t ka, uint32_t kb, size_t n, float* out) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        Rng rng; rng.init(keys, ka, kb);
-        for (size_t i = 0; i < n; ++i) out[i] = rng.gen();
-    }
-}
-
-// FP32 issue ceiling: 8 independent FFMA chains per thread.
-__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float b, float c) {
-    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-#pragma unroll 1
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            x0 = fmaf(x0, b, c); x1 = fmaf(x1, b, c); x2 = fmaf(x2, b, c); x3 = fmaf(x3, b, c);
-            x4 = fmaf(x4, b, c); x5 = fmaf(x5, b, c); x6 = fmaf(x6, b, c); x7 = fmaf(x7, b, c);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
-}
-
 }  // namespace b200rt
+
+#include "render_kernel.cuh"
+#include "render_variants.cuh"
+#include "aux_kernels.cuh"
+
 
 // ==========================================================================================
 // host side of the C ABI

@@ -1,0 +1,332 @@
+// render_kernel.cuh — K2: kernel arguments, scene staging and the persistent path-tracing kernel (path_trace_kernel_v2), the default
+// (included by b200rt.cu; everything lives in namespace b200rt)
+#pragma once
+#include "rt_device.cuh"
+
+namespace b200rt {
+
+// ------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------
+constexpr int BLOCK = 256;          // threads per CTA (8 warps)
+constexpr size_t LBVH_AUTO_MIN = 262144;   // primitives from which scene_create builds the tree on the device
+constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
+
+struct SmemPlan {
+    uint32_t all_in_smem;           // 1: nodes + geom + mats + tex all staged (SmemAcc)
+    uint32_t n_top;                 // nodes staged when !all_in_smem
+    uint32_t stack_depth;           // entries per thread
+    uint32_t bytes;                 // dynamic shared memory per CTA
+};
+
+struct Counters {                   // device-side, one per in-flight render
+    unsigned long long rays, paths, nodes, prims, exhausted;
+    unsigned int tile_counter, pad;
+    unsigned long long diag[8];
+};
+
+struct RenderArgs {
+    DeviceScene scene;
+    DeviceCamera cam;
+    SmemPlan plan;
+    RngKeys keys;
+    uint32_t samples, sample_offset, max_depth;
+    uint32_t row_begin, row_end;
+    uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
+    uint32_t shard_count, shard_index;
+    uint32_t accumulate;
+    uint32_t trav_threshold;                    // v2: leave the traversal loop when fewer lanes than this still traverse
+    uint32_t wf_inner, wf_fetch, wf_park;       // v3 thresholds (see path_trace_kernel_v3)
+    float4* accum;
+    Counters* counters;
+};
+
+__device__ __forceinline__ TopPrims top_of(const DeviceScene& s) {
+    TopPrims t; t.n = s.n_top_prims;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t.code[k] = s.top_prims[k];
+    return t;
+}
+
+// Stage the scene (or the top of the BVH) into shared memory and set up the accessor.
+// Shared layout: [nodes][geom][mats][tex][stack: stack_depth x BLOCK ints]
+template <class Acc> struct Stager;
+template <> struct Stager<SmemAcc> {
+    static __device__ __forceinline__ SmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
+        uint32_t n_nodes4 = s.n_nodes * 4, n_geom4 = s.n_prims * 2, n_mat4 = s.n_prims * 2, n_tex4 = s.n_tex * 2;
+        float4* nodes = smem;
+        float4* geom = nodes + n_nodes4;
+        float4* mats = geom + n_geom4;
+        float4* tex = mats + n_mat4;
+        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
+        const float4* gg = reinterpret_cast<const float4*>(s.geom);
+        const float4* gm = reinterpret_cast<const float4*>(s.mats);
+        const float4* gt = reinterpret_cast<const float4*>(s.tex);
+        for (uint32_t i = threadIdx.x; i < n_nodes4; i += blockDim.x) nodes[i] = __ldg(gn + i);
+        for (uint32_t i = threadIdx.x; i < n_geom4; i += blockDim.x) geom[i] = __ldg(gg + i);
+        for (uint32_t i = threadIdx.x; i < n_mat4; i += blockDim.x) mats[i] = __ldg(gm + i);
+        for (uint32_t i = threadIdx.x; i < n_tex4; i += blockDim.x) tex[i] = __ldg(gt + i);
+        *stack = reinterpret_cast<int*>(tex + n_tex4);
+        __syncthreads();
+        SmemAcc a; a.nodes = nodes; a.geom = geom; a.mats = mats; a.tex = tex;
+        return a;
+    }
+};
+template <> struct Stager<GmemAcc> {
+    static __device__ __forceinline__ GmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
+        uint32_t n_top4 = plan.n_top * 4;
+        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
+        for (uint32_t i = threadIdx.x; i < n_top4; i += blockDim.x) smem[i] = __ldg(gn + i);
+        *stack = reinterpret_cast<int*>(smem + n_top4);
+        __syncthreads();
+        GmemAcc a;
+        a.nodes = gn; a.geom = reinterpret_cast<const float4*>(s.geom);
+        a.mats = reinterpret_cast<const float4*>(s.mats); a.tex = reinterpret_cast<const float4*>(s.tex);
+        a.top = smem; a.n_top = (int)plan.n_top;
+        return a;
+    }
+};
+
+constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + stream, tile pixel
+
+// Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
+// result does not depend on which lane traced which sample, nor on scheduling or sharding.
+__device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v) {
+    // 2^-32 fixed point; non-finite contributions are dropped (a NaN sample would blacken the
+    // reference's pixel; here it contributes nothing)
+    const float S = 4294967296.0f;
+    if (fabsf(v.x + v.y + v.z) <= 3.0e38f) {   // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative)
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (v2): the same persistent kernel restructured for SIMT efficiency (ncu on v1: 8.1 of 32
+// lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble
+// texture at 2.7):
+//  * while-while traversal: every lane runs inner-node visits until it holds a leaf, then the
+//    warp tests the postponed leaves together;
+//  * the traversal cursor is resumable, and the warp leaves the traversal loop as soon as
+//    fewer than `trav_threshold` lanes are still traversing: finished lanes shade, scatter and
+//    start their next segment (or next sample) instead of idling until the slowest lane ends;
+//  * scene-spanning primitives are tested up front, uniformly (DeviceScene::top_prims);
+//  * the Perlin marble is evaluated by the whole warp (coop_turbulence);
+//  * one-FMA slab planes against padded boxes (FAST).
+// ------------------------------------------------------------------------------------------
+template <class Acc, bool COUNT, bool FAST, int BLK, int MINB>
+__global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_constant__ RenderArgs a) {
+    extern __shared__ float4 smem[];
+    int* stack_base;
+    Acc acc = Stager<Acc>::stage(a.scene, a.plan, smem, &stack_base);
+    int* stack = stack_base + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    // per-warp fixed-point accumulators [32 pixels][3] behind the stack columns
+    long long* wacc = reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (threadIdx.x >> 5) * 96;
+    // per-warp queue of generated primary rays, SoA [RAYQ_FIELDS][RAYQ_SLOTS] behind the accumulators
+    uint32_t* rayq = reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
+                     + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
+    const float T_MIN = 0.001f;                      // render.rs:31
+    const bool has_perlin = a.scene.perlin != nullptr;
+
+    unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
+    // lane-utilisation diagnostics (COUNT only, lane 0 of each warp):
+    //  d0 outer iterations, d1 sum of alive lanes, d2 sum of lanes with no samples left,
+    //  d3 traversal rounds, d4 sum of traversing lanes per round, d5 sum of lanes shaded,
+    //  d6 sum of lanes regenerated, d7 inner-node visit steps (warp-level)
+    unsigned long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0, d5 = 0, d6 = 0, d7 = 0;
+
+    for (;;) {
+        unsigned int j = 0;
+        if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
+        j = __shfl_sync(FULL, j, 0);
+        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
+        if (t64 >= a.n_tiles) break;
+        uint32_t t = (uint32_t)t64;
+        uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
+        const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
+        const bool valid = my_px < a.cam.width && my_py >= a.row_begin && my_py < a.row_end;
+        // The tile's work list: item i = sample * nv + k (k-th valid pixel).  Any lane takes the
+        // next item when its path ends, so all lanes stay busy until the tile is finished
+        // (with lane = pixel, 17 % of the lanes sat out of samples at tile ends).
+        const unsigned valid_mask = __ballot_sync(FULL, valid);
+        const uint32_t nv = (uint32_t)__popc(valid_mask);
+        const uint32_t n_items = a.samples * nv;
+        uint32_t next_item = 0;          // next work-list item to generate
+        uint32_t q_head = 0, q_count = 0;  // the warp's ring of generated primary rays
+        for (int k = lane; k < 96; k += 32) wacc[k] = 0;
+        __syncwarp();
+        uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
+        uint32_t nrays = 0, nexh = 0;   // nrays: warp total (same value in every lane), nexh: per lane
+        TravCounters tc; tc.nodes = 0; tc.prims = 0;
+        bool alive = false;
+        Rng rng; rng.state = 0; rng.inc = 1;
+        RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
+        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
+        uint32_t depth = 0;
+        int node = B200RT_TRAV_DONE;
+        const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
+        uint32_t top_sp = stack_s + BLK * 4;   // shared-window address of the next free slot of this lane's stack column
+        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+        stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
+
+        // One outer iteration = shade the lanes whose traversal finished, hand new paths to the
+        // lanes without one, set up the new segments of BOTH groups together (one copy of the ray
+        // set-up + up-front primitive code, run at ~30 lanes instead of twice at 6 and 18), traverse.
+        for (;;) {
+            // ---- shade: ray_color's loop body, render.rs:31-46 ----
+            bool fin = alive && node == B200RT_TRAV_DONE;
+            if (COUNT) { d0 += 1; d5 += __popc(__ballot_sync(FULL, fin)); }
+            bool hit = fin && c.code >= 0;
+            bool done = false, setup = false;
+            HitRec h;
+            ShadePrep sp_;
+            sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
+            h.p = f3(0.f, 0.f, 0.f);
+            if (fin && !hit) {
+                emit = emit + atten * background(a.scene, ray.d);
+                done = true;
+            }
+            if (hit) {
+                h = make_hit(ray, acc, c);
+                sp_ = shade_prepare(a.scene, acc, h);
+            }
+            float turb = 0.0f;
+            if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))   // warp-uniform: skip the call when no lane asks
+                turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+            if (hit) {
+                float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
+                ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
+                done = !so.scattered;
+                if (!done) {
+                    if (--depth == 0) { done = true; ++nexh; }
+                    else { ray.o = so.o; ray.d = so.d; setup = true; }
+                }
+            }
+            if (done) { acc_add(wacc, pl, emit); alive = false; }
+
+            // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
+            // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG
+            // keying, jitter, lens rejection loop, Camera::pixel_ray) and handed out to the ~6 lanes
+            // per iteration whose path ended; generating them on demand ran that code at 6 lanes.
+            unsigned want_m = __ballot_sync(FULL, !alive);
+            const uint32_t want = (uint32_t)__popc(want_m);
+            if (q_count < want && next_item < n_items) {           // warp-uniform
+                __syncwarp();
+                // top the ring up to 32 entries: the first (32 - q_count) lanes generate
+                const uint32_t n_new = min(RAYQ_SLOTS - q_count, n_items - next_item);
+                uint32_t item = next_item + (uint32_t)lane;
+                if ((uint32_t)lane < n_new) {
+                    uint32_t sidx = (nv == 32u) ? (item >> 5) : item / nv;
+                    uint32_t kth = item - sidx * nv;
+                    uint32_t qpl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
+                    uint32_t px = px0 + (qpl & (TILE_W - 1)), py = py0 + (qpl >> 3);
+                    Rng qr;
+                    qr.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                    float jx = (float)px + qr.gen();
+                    float jy = (float)py + qr.gen();
+                    float3 qo, qd;
+                    pixel_ray(a.cam, qr, jx, jy, &qo, &qd);
+                    uint32_t slot = (q_head + q_count + (uint32_t)lane) & (RAYQ_SLOTS - 1);
+                    rayq[0 * RAYQ_SLOTS + slot] = __float_as_uint(qo.x); rayq[1 * RAYQ_SLOTS + slot] = __float_as_uint(qo.y);
+                    rayq[2 * RAYQ_SLOTS + slot] = __float_as_uint(qo.z); rayq[3 * RAYQ_SLOTS + slot] = __float_as_uint(qd.x);
+                    rayq[4 * RAYQ_SLOTS + slot] = __float_as_uint(qd.y); rayq[5 * RAYQ_SLOTS + slot] = __float_as_uint(qd.z);
+                    rayq[6 * RAYQ_SLOTS + slot] = qr.state; rayq[7 * RAYQ_SLOTS + slot] = qr.inc; rayq[8 * RAYQ_SLOTS + slot] = qpl;
+                }
+                next_item += n_new; q_count += n_new;
+                __syncwarp();
+            }
+            const uint32_t rank = (uint32_t)__popc(want_m & lt);
+            bool regen = !alive && rank < q_count;
+            if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
+            if (regen) {
+                uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);
+                ray.o = f3(__uint_as_float(rayq[0 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[1 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[2 * RAYQ_SLOTS + slot]));
+                ray.d = f3(__uint_as_float(rayq[3 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[4 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[5 * RAYQ_SLOTS + slot]));
+                rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot]; pl = rayq[8 * RAYQ_SLOTS + slot];
+                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
+                depth = a.max_depth;
+                alive = depth > 0;
+                setup = alive;
+            }
+            {
+                uint32_t taken = min(want, q_count);
+                q_head = (q_head + taken) & (RAYQ_SLOTS - 1); q_count -= taken;
+            }
+            if (!__any_sync(FULL, alive)) break;
+            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
+
+            // ---- new segment: per-ray constants, then the scene-spanning primitives ----
+            if (setup) {
+                // IEEE reciprocals, taken once: the up-front rect/box tests need exactly these
+                // (bit-reproducible on the CPU), and the slab tests take them too
+                float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
+                ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
+                ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
+                ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
+                c.t = INFINITY; c.code = -1; c.face = 0;
+                // the list is indexed in the kernel parameters (constant bank): a register copy indexed by a
+                // loop counter would live in local memory
+#pragma unroll 1
+                for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
+                    if (COUNT) tc.prims++;
+                    hit_leaf(ray, acc, a.scene.top_prims[k], T_MIN, c, &inv_e);
+                }
+                node = 0; top_sp = stack_s + BLK * 4;
+            }
+            nrays += (uint32_t)__popc(__ballot_sync(FULL, setup));   // warp-uniform count: no per-lane counter to keep live
+
+            // ---- traversal: BboxTree::hit_workspace, bvh/bbox_tree.rs:56-91 ----
+            for (;;) {
+                if (COUNT) { d3 += 1; d4 += __popc(__ballot_sync(FULL, node != B200RT_TRAV_DONE)); }
+                // (a warp-uniform inner loop that stops below a lane threshold, and a cap on the steps per
+                //  round, were measured: 15-18 lanes per step instead of 13.6, but no faster — profiles/README.md)
+                while (node >= 0 && node != B200RT_TRAV_DONE) {
+                    if (COUNT) d7 += (__ffs(__activemask()) - 1 == lane) ? 1 : 0;
+                    trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
+                }
+                if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLK * 4, T_MIN, c, node, tc);
+                unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
+                if ((uint32_t)__popc(still) < a.trav_threshold) break;
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            const float inv = 1.0f / 4294967296.0f;
+            float4* dst = a.accum + (my_py * a.cam.width + my_px);
+            float4 v = make_float4((float)wacc[lane * 3 + 0] * inv, (float)wacc[lane * 3 + 1] * inv, (float)wacc[lane * 3 + 2] * inv, (float)a.samples);
+            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
+        __syncwarp();
+        w_rays += lane == 0 ? nrays : 0u; w_exh += nexh; w_paths += lane == 0 ? n_items : 0u;   // every work-list item became one path
+        if (COUNT) { w_nodes += tc.nodes; w_prims += tc.prims; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        w_rays += __shfl_down_sync(FULL, w_rays, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o);
+        w_exh += __shfl_down_sync(FULL, w_exh, o);
+        if (COUNT) { w_nodes += __shfl_down_sync(FULL, w_nodes, o); w_prims += __shfl_down_sync(FULL, w_prims, o); }
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters->rays, w_rays);
+        atomicAdd(&a.counters->paths, w_paths);
+        atomicAdd(&a.counters->exhausted, w_exh);
+        if (COUNT) { atomicAdd(&a.counters->nodes, w_nodes); atomicAdd(&a.counters->prims, w_prims); }
+    }
+    if (COUNT) {
+        // d7 was counted by whichever lane led each divergent step: sum it over the warp
+        for (int o = 16; o > 0; o >>= 1) d7 += __shfl_down_sync(FULL, d7, o);
+        if (lane == 0) {
+            atomicAdd(&a.counters->diag[0], d0); atomicAdd(&a.counters->diag[1], d1); atomicAdd(&a.counters->diag[2], d2); atomicAdd(&a.counters->diag[3], d3);
+            atomicAdd(&a.counters->diag[4], d4); atomicAdd(&a.counters->diag[5], d5); atomicAdd(&a.counters->diag[6], d6); atomicAdd(&a.counters->diag[7], d7);
+        }
+    }
+}
+
+
+}  // namespace b200rt
