@@ -38,12 +38,15 @@ const B200rtSceneDesc* b200rt_host_scene_desc(const B200rtHostScene* scene);
 /* Decoded RGB8 pixels for TextureLoader::EarthBuiltin (name "EarthBuiltin") or
  * ImagePath(name) (image_texture.rs:18-31); a registration takes precedence over decoding. */
 int  b200rt_host_register_image(const char* name, uint32_t width, uint32_t height, const uint8_t* rgb8);
-/* image::load_from_memory for a baseline JPEG (image_texture.rs:18-21,28-31): RGB8 pixels, top row
+/* image::load_from_memory for a JPEG, baseline or progressive (image_texture.rs:18-21,28-31): RGB8 pixels, top row
  * first, in a buffer to release with b200rt_free.  ImagePath textures that were not registered
  * are decoded with the same routine at finalize; EarthBuiltin is decoded from the file named by
  * the environment variable B200RT_EARTHMAP (a copy of the reference's assets/earthmap.jpg) when
  * set, else it is the procedural stand-in. */
 int  b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint8_t** rgb8);
+/* The same for any format decoded here — JPEG or PNG (8-bit grey / grey+alpha / RGB / RGBA / palette,
+ * non-interlaced; alpha dropped) — sniffed from the first bytes like image::load_from_memory. */
+int  b200rt_host_decode_image(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint8_t** rgb8);
 
 /* CameraBuilder + CameraPosition::look_at (camera/mod.rs:23-85).  aperture < 0 = None;
  * focus_length <= 0 keeps look_at's |camera - target|.  Exactly two of

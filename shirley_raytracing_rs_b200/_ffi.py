@@ -154,6 +154,7 @@ SIGNATURES = {
     "b200rt_host_scene_destroy": (None, [C.c_void_p]),
     "b200rt_host_scene_desc": (_P(SceneDesc), [C.c_void_p]),
     "b200rt_host_register_image": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "b200rt_host_decode_image": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_void_p)]),
     "b200rt_host_decode_jpeg": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_void_p)]),
     "b200rt_host_checkpoint_save": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]),
     "b200rt_host_checkpoint_load": (C.c_int, [C.c_char_p, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint64), _P(C.c_void_p)]),

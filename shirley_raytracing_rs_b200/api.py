@@ -259,11 +259,11 @@ def register_image(name: str, rgb: np.ndarray) -> None:
     F.check(lib.b200rt_host_register_image(name.encode(), w, h, rgb.ctypes.data), host=True)
 
 
-def decode_jpeg(data: bytes) -> np.ndarray:
-    """image::load_from_memory for a baseline JPEG (image_texture.rs:18-21): (H, W, 3) uint8."""
+def decode_image(data: bytes) -> np.ndarray:
+    """image::load_from_memory (image_texture.rs:18-21) for a JPEG or PNG: (H, W, 3) uint8, alpha dropped."""
     buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
     w, h, out = C.c_uint32(), C.c_uint32(), C.c_void_p()
-    F.check(lib.b200rt_host_decode_jpeg(buf, len(data), C.byref(w), C.byref(h), C.byref(out)), host=True)
+    F.check(lib.b200rt_host_decode_image(buf, len(data), C.byref(w), C.byref(h), C.byref(out)), host=True)
     try:
         return np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(h.value, w.value, 3)).copy()
     finally:
@@ -287,6 +287,9 @@ def checkpoint_load(path: str):
     finally:
         lib.b200rt_free(out)
     return acc, n.value, seed.value
+
+
+decode_jpeg = decode_image
 
 
 # ---- camera (camera/mod.rs) -------------------------------------------------------------------------

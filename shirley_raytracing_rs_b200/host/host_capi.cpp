@@ -89,13 +89,18 @@ int b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, u
     if (!data || !width || !height || !rgb8) return host_fail(B200RT_EINVAL, "NULL argument");
     *rgb8 = nullptr;
     try {
-        scene::ImageData img = scene::decode_jpeg(data, size);
+        // image::load_from_memory sniffs the format: JPEG or PNG here
+        scene::ImageData img = (size >= 8 && data[0] == 0x89 && data[1] == 'P') ? scene::decode_png(data, size) : scene::decode_jpeg(data, size);
         uint8_t* buf = (uint8_t*)malloc(img.rgb.size() ? img.rgb.size() : 1);
         if (!buf) return host_fail(B200RT_ENOMEM, "out of memory");
         memcpy(buf, img.rgb.data(), img.rgb.size());
         *width = img.width; *height = img.height; *rgb8 = buf;
         return B200RT_OK;
     } catch (const std::exception& e) { return host_fail(B200RT_EINVAL, e.what()); }
+}
+
+int b200rt_host_decode_image(const uint8_t* data, size_t size, uint32_t* width, uint32_t* height, uint8_t** rgb8) {
+    return b200rt_host_decode_jpeg(data, size, width, height, rgb8);   // one sniffing implementation
 }
 
 int b200rt_host_checkpoint_save(const char* path, const float* accum, uint32_t W, uint32_t H, uint32_t samples_done, uint64_t seed) {

@@ -4,14 +4,14 @@
 // (material/texture/image_texture.rs:23-31; crate image 0.24.3 -> jpeg-decoder 0.2.6, not
 // vendored under /root/reference) and reads texels as RGB8 (image_texture.rs:44-55).  No JPEG
 // library headers exist in this image, so this is a from-scratch decoder of the subset the
-// texture path needs: baseline sequential DCT (SOF0/SOF1), 8-bit, Huffman, 1 or 3 components,
-// restart intervals, JFIF YCbCr or Adobe RGB.  Arithmetic follows the published libjpeg
+// texture path needs: sequential (SOF0/SOF1) and progressive (SOF2) DCT, 8-bit, Huffman, 1 or 3 components,
+// any scan script, restart intervals, JFIF YCbCr or Adobe RGB.  Arithmetic follows the published libjpeg
 // algorithms — the accurate integer inverse DCT ("islow", 13-bit constants), the 16-bit
 // fixed-point YCbCr->RGB tables and the triangle-filter ("fancy") chroma upsampling for 2x1 and
 // 2x2 subsampling — so that the bytes agree with libjpeg-based decoders (PIL, OpenCV), which
 // tests/test_jpeg.py checks.  jpeg-decoder's own IDCT may differ by +-1 level on some texels;
 // assets/earthmap.jpg is 4:4:4 baseline, where only the IDCT rounding is in play.
-// Progressive (SOF2) and arithmetic-coded files are rejected with an error.
+// Arithmetic-coded, lossless and hierarchical files are rejected with an error.
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -60,6 +60,7 @@ struct Component {
     int blocks_w = 0, blocks_h = 0;     // allocated blocks (whole MCUs)
     int width = 0, height = 0;          // downsampled size in samples: ceil(image * h / hmax)
     std::vector<uint8_t> plane;         // blocks_w*8 x blocks_h*8 samples
+    std::vector<int16_t> coef;          // blocks_w x blocks_h blocks of 64 coefficients, natural order
     int dc_pred = 0;
 };
 
@@ -146,6 +147,105 @@ uint16_t rd16(const uint8_t* p) { return (uint16_t)((p[0] << 8) | p[1]); }
 
 }  // namespace
 
+namespace {
+
+// One scan of entropy-coded data (T.81 F.2 sequential, G.1 progressive).  Coefficients accumulate in the
+// components' `coef` arrays (natural order, 64 per block); the inverse DCT runs once after the last scan.
+struct Scan {
+    std::vector<Component*> comps;
+    int Ss = 0, Se = 63, Ah = 0, Al = 0;
+    bool progressive = false;
+};
+
+struct ScanDecoder {
+    BitReader br;
+    const HuffTable* dc; const HuffTable* ac;   // arrays of 4
+    const Scan& sc;
+    int eobrun = 0;
+    ScanDecoder(const HuffTable* d, const HuffTable* a, const Scan& s) : dc(d), ac(a), sc(s) {}
+
+    void block_sequential(Component& c, int16_t* blk) {                       // F.2.2
+        int t = decode_symbol(br, dc[c.td]);
+        if (t > 11) throw Error("jpeg: bad DC category");
+        c.dc_pred += t ? extend(br.get(t), t) : 0;
+        blk[0] = (int16_t)c.dc_pred;
+        for (int k = 1; k < 64;) {
+            int rs = decode_symbol(br, ac[c.ta]);
+            int r = rs >> 4, s = rs & 15;
+            if (s == 0) { if (r == 15) { k += 16; continue; } break; }       // ZRL / EOB
+            k += r;
+            if (k > 63) throw Error("jpeg: AC coefficient index out of range");
+            blk[ZIGZAG[k]] = (int16_t)extend(br.get(s), s);
+            ++k;
+        }
+    }
+    void block_dc_first(Component& c, int16_t* blk) {                         // G.1.2.1
+        int t = decode_symbol(br, dc[c.td]);
+        if (t > 11) throw Error("jpeg: bad DC category");
+        c.dc_pred += t ? extend(br.get(t), t) : 0;
+        blk[0] = (int16_t)(c.dc_pred * (1 << sc.Al));
+    }
+    void block_dc_refine(int16_t* blk) { if (br.get(1)) blk[0] = (int16_t)(blk[0] | (1 << sc.Al)); }
+    void block_ac_first(Component& c, int16_t* blk) {                         // G.1.2.2
+        if (eobrun > 0) { --eobrun; return; }
+        for (int k = sc.Ss; k <= sc.Se; ++k) {
+            int rs = decode_symbol(br, ac[c.ta]);
+            int r = rs >> 4, s = rs & 15;
+            if (s) {
+                k += r;
+                if (k > 63) throw Error("jpeg: AC coefficient index out of range");
+                blk[ZIGZAG[k]] = (int16_t)(extend(br.get(s), s) * (1 << sc.Al));
+            } else if (r == 15) {
+                k += 15;
+            } else {
+                eobrun = 1 << r;
+                if (r) eobrun += br.get(r);
+                --eobrun;
+                break;
+            }
+        }
+    }
+    void block_ac_refine(Component& c, int16_t* blk) {                        // G.1.2.3
+        const int p1 = 1 << sc.Al, m1 = -(1 << sc.Al);
+        int k = sc.Ss;
+        auto correct = [&](int16_t& coef) {
+            if (br.get(1) && (coef & p1) == 0) coef = (int16_t)(coef + (coef >= 0 ? p1 : m1));
+        };
+        if (eobrun == 0) {
+            for (; k <= sc.Se; ++k) {
+                int rs = decode_symbol(br, ac[c.ta]);
+                int r = rs >> 4, s = rs & 15;
+                if (s) {
+                    if (s != 1) throw Error("jpeg: bad refinement symbol");
+                    s = br.get(1) ? p1 : m1;
+                } else if (r != 15) {
+                    eobrun = 1 << r;
+                    if (r) eobrun += br.get(r);
+                    break;                                                    // the rest of the band is handled below
+                }
+                // skip r zero-history coefficients, correcting the non-zero ones passed on the way
+                for (; k <= sc.Se; ++k) {
+                    int16_t& coef = blk[ZIGZAG[k]];
+                    if (coef != 0) correct(coef);
+                    else if (--r < 0) break;
+                }
+                if (s && k <= sc.Se) blk[ZIGZAG[k]] = (int16_t)s;
+            }
+        }
+        if (eobrun > 0) {
+            for (; k <= sc.Se; ++k) { int16_t& coef = blk[ZIGZAG[k]]; if (coef != 0) correct(coef); }
+            --eobrun;
+        }
+    }
+    void block(Component& c, int16_t* blk) {
+        if (!sc.progressive) block_sequential(c, blk);
+        else if (sc.Ss == 0) { if (sc.Ah == 0) block_dc_first(c, blk); else block_dc_refine(blk); }
+        else { if (sc.Ah == 0) block_ac_first(c, blk); else block_ac_refine(c, blk); }
+    }
+};
+
+}  // namespace
+
 ImageData decode_jpeg(const uint8_t* data, size_t size) {
     if (size < 4 || data[0] != 0xFF || data[1] != 0xD8) throw Error("jpeg: missing SOI marker");
     uint16_t qt[4][64]; bool qt_def[4] = {false, false, false, false};
@@ -153,7 +253,7 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
     std::vector<Component> comps;
     int W = 0, H = 0, hmax = 1, vmax = 1, restart_interval = 0;
     bool adobe = false; int adobe_transform = -1; bool jfif = false;
-    bool have_frame = false, done = false;
+    bool have_frame = false, progressive = false, done = false, any_scan = false;
     size_t pos = 2;
     int mcus_x = 0, mcus_y = 0;
 
@@ -163,8 +263,8 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
         while (pos < size && data[pos] == 0xFF) ++pos;
         if (pos >= size) break;
         int m = data[pos++];
-        if (m == 0xD9) break;                                   // EOI
-        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;      // TEM / stray RSTn
+        if (m == 0xD9) break;                                             // EOI
+        if (m == 0x00 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;   // stuffed byte left over from a scan / TEM / stray RSTn
         if (pos + 2 > size) throw Error("jpeg: truncated segment");
         size_t len = rd16(data + pos);
         if (len < 2 || pos + len > size) throw Error("jpeg: bad segment length");
@@ -178,7 +278,7 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
                     if (i + (pq ? 128 : 64) > n) throw Error("jpeg: truncated DQT");
                     for (int k = 0; k < 64; ++k) {
                         uint16_t v = pq ? rd16(seg + i + 2 * k) : seg[i + k];
-                        qt[tq][ZIGZAG[k]] = v;                    // store in natural order
+                        qt[tq][ZIGZAG[k]] = v;                            // store in natural order
                     }
                     i += pq ? 128 : 64; qt_def[tq] = true;
                 }
@@ -201,9 +301,11 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
                 }
                 break;
             }
-            case 0xC0: case 0xC1: {   // SOF0 / SOF1 (Huffman, sequential)
+            case 0xC0: case 0xC1: case 0xC2: {   // SOF0 / SOF1 (sequential) / SOF2 (progressive), Huffman
+                if (have_frame) throw Error("jpeg: more than one frame header");
                 if (n < 6) throw Error("jpeg: truncated SOF");
                 if (seg[0] != 8) throw Error("jpeg: only 8-bit samples are supported");
+                progressive = m == 0xC2;
                 H = rd16(seg + 1); W = rd16(seg + 3);
                 int nc = seg[5];
                 if (W == 0 || H == 0) throw Error("jpeg: empty image");
@@ -221,11 +323,11 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
                     c.blocks_w = mcus_x * c.h; c.blocks_h = mcus_y * c.v;
                     c.width = (W * c.h + hmax - 1) / hmax; c.height = (H * c.v + vmax - 1) / vmax;
                     c.plane.assign((size_t)c.blocks_w * 8 * c.blocks_h * 8, 0);
+                    c.coef.assign((size_t)c.blocks_w * c.blocks_h * 64, 0);
                 }
                 have_frame = true;
                 break;
             }
-            case 0xC2: throw Error("jpeg: progressive JPEG is not supported (baseline only)");
             case 0xC3: case 0xC5: case 0xC6: case 0xC7: case 0xC9: case 0xCA: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
                 throw Error("jpeg: unsupported coding process (lossless / hierarchical / arithmetic)");
             case 0xDD: if (n < 2) throw Error("jpeg: truncated DRI"); restart_interval = rd16(seg); break;
@@ -234,63 +336,67 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
             case 0xDA: {   // SOS + entropy-coded data
                 if (!have_frame) throw Error("jpeg: scan before frame header");
                 int ns = seg[0];
-                if (ns != (int)comps.size()) throw Error("jpeg: only single-scan (fully interleaved) baseline files are supported");
-                if (n < (size_t)(1 + 2 * ns + 3)) throw Error("jpeg: truncated SOS");
+                if (ns < 1 || ns > (int)comps.size() || n < (size_t)(1 + 2 * ns + 3)) throw Error("jpeg: bad SOS");
+                Scan sc; sc.progressive = progressive;
                 for (int s = 0; s < ns; ++s) {
-                    int id = seg[1 + 2 * s]; bool found = false;
-                    for (auto& c : comps) if (c.id == id) { c.td = seg[2 + 2 * s] >> 4; c.ta = seg[2 + 2 * s] & 15; found = true; }
+                    int id = seg[1 + 2 * s]; Component* found = nullptr;
+                    for (auto& c : comps) if (c.id == id) found = &c;
                     if (!found) throw Error("jpeg: scan names an unknown component");
+                    found->td = seg[2 + 2 * s] >> 4; found->ta = seg[2 + 2 * s] & 15;
+                    if (found->td > 3 || found->ta > 3) throw Error("jpeg: bad Huffman table selector");
+                    sc.comps.push_back(found);
                 }
-                for (auto& c : comps) {
-                    if (c.td > 3 || c.ta > 3 || !dc[c.td].defined || !ac[c.ta].defined) throw Error("jpeg: scan uses an undefined Huffman table");
-                    if (!qt_def[c.tq]) throw Error("jpeg: component uses an undefined quantisation table");
-                    c.dc_pred = 0;
+                sc.Ss = seg[1 + 2 * ns]; sc.Se = seg[2 + 2 * ns]; sc.Ah = seg[3 + 2 * ns] >> 4; sc.Al = seg[3 + 2 * ns] & 15;
+                if (!progressive) { sc.Ss = 0; sc.Se = 63; sc.Ah = sc.Al = 0; }
+                if (sc.Ss > sc.Se || sc.Se > 63 || sc.Al > 13 || (progressive && sc.Ss > 0 && ns != 1) || (progressive && sc.Ss == 0 && sc.Se != 0))
+                    throw Error("jpeg: bad progressive scan parameters");
+                const bool need_dc = !progressive || (sc.Ss == 0 && sc.Ah == 0), need_ac = !progressive || sc.Ss > 0;
+                for (Component* c : sc.comps) {
+                    if ((need_dc && !dc[c->td].defined) || (need_ac && !ac[c->ta].defined)) throw Error("jpeg: scan uses an undefined Huffman table");
+                    if (!qt_def[c->tq]) throw Error("jpeg: component uses an undefined quantisation table");
+                    c->dc_pred = 0;
                 }
-                BitReader br; br.p = data + pos + len; br.end = data + size;
-                int16_t block[64];
+                ScanDecoder dec(dc, ac, sc);
+                dec.br.p = data + pos + len; dec.br.end = data + size;
+                // an interleaved scan walks MCUs; a single-component scan walks that component's own blocks (A.2.3)
+                const bool interleaved = ns > 1;
+                Component& c0 = *sc.comps[0];
+                const int units_x = interleaved ? mcus_x : (c0.width + 7) / 8, units_y = interleaved ? mcus_y : (c0.height + 7) / 8;
                 int until_restart = restart_interval, next_rst = 0;
-                for (int my = 0; my < mcus_y; ++my) for (int mx = 0; mx < mcus_x; ++mx) {
+                for (int uy = 0; uy < units_y; ++uy) for (int ux = 0; ux < units_x; ++ux) {
                     if (restart_interval && until_restart == 0) {
-                        // expect RSTn at the byte position (after any fill bits)
-                        br.reset();
-                        const uint8_t* p = br.p;
-                        while (p + 1 < br.end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
-                        if (p + 1 >= br.end) throw Error("jpeg: missing restart marker");
+                        dec.br.reset();
+                        const uint8_t* p = dec.br.p;
+                        while (p + 1 < dec.br.end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
+                        if (p + 1 >= dec.br.end) throw Error("jpeg: missing restart marker");
                         if ((p[1] & 7) != next_rst) throw Error("jpeg: restart markers out of order");
                         next_rst = (next_rst + 1) & 7;
-                        br.p = p + 2;
-                        for (auto& c : comps) c.dc_pred = 0;
+                        dec.br.p = p + 2;
+                        for (Component* c : sc.comps) c->dc_pred = 0;
+                        dec.eobrun = 0;
                         until_restart = restart_interval;
                     }
-                    for (auto& c : comps) for (int by = 0; by < c.v; ++by) for (int bx = 0; bx < c.h; ++bx) {
-                        memset(block, 0, sizeof block);
-                        int t = decode_symbol(br, dc[c.td]);
-                        if (t > 11) throw Error("jpeg: bad DC category");
-                        int diff = t ? extend(br.get(t), t) : 0;
-                        c.dc_pred += diff;
-                        block[0] = (int16_t)c.dc_pred;
-                        for (int k = 1; k < 64;) {
-                            int rs = decode_symbol(br, ac[c.ta]);
-                            int r = rs >> 4, s = rs & 15;
-                            if (s == 0) { if (r == 15) { k += 16; continue; } break; }   // ZRL / EOB
-                            k += r;
-                            if (k > 63) throw Error("jpeg: AC coefficient index out of range");
-                            block[ZIGZAG[k]] = (int16_t)extend(br.get(s), s);
-                            ++k;
-                        }
-                        int px = (mx * c.h + bx) * 8, py = (my * c.v + by) * 8;
-                        idct_islow(block, qt[c.tq], c.plane.data() + (size_t)py * c.blocks_w * 8 + px, c.blocks_w * 8);
+                    if (interleaved) {
+                        for (Component* c : sc.comps) for (int by = 0; by < c->v; ++by) for (int bx = 0; bx < c->h; ++bx)
+                            dec.block(*c, &c->coef[((size_t)(uy * c->v + by) * c->blocks_w + (ux * c->h + bx)) * 64]);
+                    } else {
+                        dec.block(c0, &c0.coef[((size_t)uy * c0.blocks_w + ux) * 64]);
                     }
                     if (restart_interval) --until_restart;
                 }
-                done = true;
-                break;
+                any_scan = true;
+                pos = (size_t)(dec.br.p - data);      // the reader never runs past a marker: resume the marker search there
+                if (!progressive && ns == (int)comps.size()) done = true;   // a fully interleaved baseline scan is the whole picture
+                continue;                              // (pos already advanced past the segment and its entropy data)
             }
             default: break;   // APPn, COM, ...: skipped
         }
         pos += len;
     }
-    if (!done) throw Error("jpeg: no scan data found");
+    if (!any_scan) throw Error("jpeg: no scan data found");
+    for (auto& c : comps)
+        for (int by = 0; by < c.blocks_h; ++by) for (int bx = 0; bx < c.blocks_w; ++bx)
+            idct_islow(&c.coef[((size_t)by * c.blocks_w + bx) * 64], qt[c.tq], c.plane.data() + (size_t)by * 8 * c.blocks_w * 8 + bx * 8, c.blocks_w * 8);
 
     ImageData img; img.width = (uint32_t)W; img.height = (uint32_t)H; img.rgb.resize((size_t)W * H * 3);
     if (comps.size() == 1) {

@@ -124,6 +124,9 @@ ImageData synthetic_earth(uint32_t width = 1024, uint32_t height = 512);   // st
 // reference's textures (image_texture.rs:18-31).  Throw Error on malformed or unsupported files.
 ImageData decode_jpeg(const uint8_t* data, size_t size);
 ImageData load_jpeg_file(const std::string& path);
+// PNG -> RGB8 (png_decoder.cpp) and the format-sniffing loader `image::open` corresponds to.
+ImageData decode_png(const uint8_t* data, size_t size);
+ImageData load_image_file(const std::string& path);
 
 // The flattened scene: owns the SoA arrays `desc` points into.
 struct Scene {

@@ -128,10 +128,10 @@ struct TextureManager {   // loader.rs:108-131
                         // the reference embeds assets/earthmap.jpg (image_texture.rs:11); that file is not part of
                         // this repository: decode it when the host points at a copy, else the procedural stand-in
                         const char* env = getenv("B200RT_EARTHMAP");
-                        if (env && *env) img = load_jpeg_file(env);
+                        if (env && *env) img = load_image_file(env);
                         else img = synthetic_earth();
                     } else {
-                        img = load_jpeg_file(t.path);   // image_texture.rs:23-26 `image::open(path)?` (baseline JPEG only here)
+                        img = load_image_file(t.path);   // image_texture.rs:23-26 `image::open(path)?` (JPEG and PNG here)
                     }
                 }
                 x.kind = B200RT_TEX_IMAGE; x.image = (int32_t)sc.image_store.size();
