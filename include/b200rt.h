@@ -239,6 +239,15 @@ int  b200rt_render_rgb8(const B200rtScene* scene, const B200rtCamera* camera,
                         const B200rtRenderParams* params, uint8_t* out_rgb8, float* accum,
                         B200rtStats* stats);
 
+/* render_scene on SEVERAL GPUs from one host process: `params->samples` is the total per pixel, split into
+ * contiguous sample ranges over `devices[0 .. n_devices)` (each gets its own copy of the scene, created by its
+ * own host thread); devices[0] sums the per-device buffers inside the resolve through peer access and returns
+ * the RGB8 frame.  The devices must be peer-accessible (NVLink / NVSwitch box).  `stats` sums rays / paths and
+ * takes the maximum of the kernel times. */
+int  b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, uint32_t n_devices,
+                              const B200rtCamera* camera, const B200rtRenderParams* params,
+                              uint8_t* out_rgb8, B200rtStats* stats);
+
 /* Same, but `d_accum` is a DEVICE pointer (float4 per pixel) on the scene's device and the
  * work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) without
  * synchronising; stats (if not NULL) are filled by b200rt_render_device_finish. Lets a

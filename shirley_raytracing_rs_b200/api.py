@@ -361,6 +361,21 @@ def render_scene(scene: Scene, cam: F.Camera, samples: int = 100, max_reflect: i
     return rgb, st
 
 
+def render_scene_multi(scene: Scene, cam: F.Camera, samples: int = 100, max_reflect: int = 50, devices: Sequence[int] = (0,),
+                       output: Optional[str] = None, seed: int = 0):
+    """render_scene on several GPUs from this one process (b200rt_render_rgb8_multi): `samples` is the total per pixel,
+    split into sample ranges over `devices`; returns (rgb8[H, W, 3], Stats)."""
+    H, W = cam.image_height, cam.image_width
+    rgb = np.empty((H, W, 3), dtype=np.uint8)
+    devs = (C.c_int * len(devices))(*devices)
+    p = F.RenderParams(samples=samples, max_depth=max_reflect, seed=seed, device=-1)
+    st = F.Stats()
+    F.check(lib.b200rt_render_rgb8_multi(scene.desc, devs, len(devices), C.byref(cam), C.byref(p), rgb.ctypes.data, C.byref(st)))
+    if output:
+        write_png(output, rgb)
+    return rgb, st
+
+
 # ---- parity hooks ------------------------------------------------------------------------------------------
 def as_rays(rays) -> np.ndarray:
     r = np.ascontiguousarray(rays, dtype=np.float32)

@@ -33,6 +33,7 @@ struct Args {
     std::string scene_output;
     uint64_t seed = 0x5EED5EEDull;
     std::string checkpoint;     // extra: accumulation-buffer checkpoint (resumed if it exists)
+    int gpus = 1;               // extra: render on the first N GPUs of this box (one process, peer access)
 };
 
 [[noreturn]] void usage(const char* msg) {
@@ -53,6 +54,7 @@ struct Args {
             "      --night                      (random) Render at night time!\n"
             "      --scene-output <FILE>        (random) Output file for scene_data\n"
             "      --seed <N>                   seed for scene generation and sampling\n"
+            "      --gpus <N>                   split the samples over the first N GPUs (NVLink peers) and sum inside the resolve\n"
             "      --checkpoint <FILE>          save the accumulation buffer there; if FILE exists, continue from it:\n"
             "                                   --samples more samples are added (same scene, camera and seed required)\n");
     exit(msg ? 2 : 0);
@@ -90,6 +92,7 @@ Args parse(int argc, char** argv) {
         else if (s == "--scene-output") a.scene_output = need("--scene-output");
         else if (s == "--seed") a.seed = strtoull(need("--seed").c_str(), nullptr, 0);
         else if (s == "--checkpoint") a.checkpoint = need("--checkpoint");
+        else if (s == "--gpus") { a.gpus = atoi(need("--gpus").c_str()); if (a.gpus < 1) usage("--gpus needs a positive count"); }
         else if (!s.empty() && s[0] == '-') usage(("unexpected argument " + s).c_str());
         else pos.push_back(s);
     }
@@ -107,6 +110,23 @@ int render_scene(const Args& args, const scene::SceneBuilder& builder, const cam
     if (samples == 0) { fprintf(stderr, " WARN  samples set to 0, using 1\n"); samples = 1; }   // main.rs:75-80
     std::unique_ptr<scene::Scene> flat = builder.finalize(args.seed ^ 0xA5A5A5A55A5A5A5Aull);
     B200rtCamera c = camera::to_abi(cam, pos);
+    if (args.gpus > 1) {                                      // one process, several GPUs: b200rt_render_rgb8_multi
+        if (!args.checkpoint.empty()) { fprintf(stderr, " ERROR --checkpoint and --gpus cannot be combined\n"); return B200RT_EINVAL; }
+        std::vector<int> devs(args.gpus);
+        for (int k = 0; k < args.gpus; ++k) devs[k] = k;
+        std::vector<uint8_t> frame((size_t)c.image_width * c.image_height * 3);
+        B200rtRenderParams mp{};
+        mp.samples = (uint32_t)samples; mp.max_depth = (uint32_t)args.max_reflect; mp.seed = args.seed; mp.device = -1;
+        B200rtStats mst{};
+        int mrc = b200rt_render_rgb8_multi(&flat->desc, devs.data(), (uint32_t)devs.size(), &c, &mp, frame.data(), &mst);
+        if (mrc) { fprintf(stderr, " ERROR %s\n", b200rt_last_error()); return mrc; }
+        if (args.verbose >= 1)
+            fprintf(stderr, " INFO  %ux%u, %zu spp on %d GPUs: %.1f ms on the slowest device, %.1f Mrays/s (%llu rays)\n", c.image_width, c.image_height, samples, args.gpus,
+                    mst.kernel_ms, (double)mst.rays / mst.kernel_ms / 1e3, (unsigned long long)mst.rays);
+        mrc = b200rt_write_png(args.output.c_str(), frame.data(), c.image_width, c.image_height);
+        if (mrc) { fprintf(stderr, " ERROR cannot write %s\n", args.output.c_str()); return mrc; }
+        return 0;
+    }
     B200rtScene* dev = nullptr;
     int rc = b200rt_scene_create(&flat->desc, -1, &dev);
     if (rc) { fprintf(stderr, " ERROR %s\n", b200rt_last_error()); return rc; }

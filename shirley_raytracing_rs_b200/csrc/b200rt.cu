@@ -22,6 +22,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh_build.hpp"
@@ -413,6 +414,8 @@ int finish_render(Scratch* scr, cudaStream_t stream, cudaEvent_t end_event, B200
 extern "C" {
 
 int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream);
+int b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers, uint32_t W, uint32_t H, uint32_t samples,
+                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, void* cuda_stream);
 
 const char* b200rt_last_error(void) { return g_last_error.c_str(); }
 int b200rt_abi_version(void) { return B200RT_ABI_VERSION; }
@@ -737,6 +740,106 @@ int b200rt_render(const B200rtScene* csc, const B200rtCamera* cam, const B200rtR
 int b200rt_render_rgb8(const B200rtScene* csc, const B200rtCamera* cam, const B200rtRenderParams* prm, uint8_t* out_rgb8, float* accum, B200rtStats* stats) {
     if (!csc || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
     return render_host_impl(csc, cam, prm, accum, out_rgb8, stats);
+}
+
+// render_scene on several GPUs from ONE host process (what a `ray-cli` user has): the scene is created on every
+// device by its own host thread, device k renders samples [k * S / N, (k + 1) * S / N) of every pixel into a buffer
+// of its own, and the first device resolves the frame with the fused sum (resolve_peers_kernel) reading the other
+// devices' buffers through peer access over NVLink.  One process per GPU + b200rt_peer_* is the other route.
+int b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, uint32_t n_devices, const B200rtCamera* cam,
+                             const B200rtRenderParams* prm, uint8_t* out_rgb8, B200rtStats* stats) {
+    if (!desc || !devices || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
+    if (n_devices < 1 || n_devices > (uint32_t)MAX_PEERS) return fail(B200RT_EINVAL, "n_devices %u outside [1, %d]", n_devices, MAX_PEERS);
+    const uint32_t total = prm->samples == 0 ? 1 : prm->samples;   // src/main.rs:75-80
+    const size_t px = (size_t)cam->image_width * cam->image_height;
+    if (px == 0) return fail(B200RT_EINVAL, "camera image dimensions are zero");
+    struct Dev { int id = 0; B200rtScene* scene = nullptr; float* accum = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; int rc = 0; std::string err; B200rtStats st{}; bool ran = false; };
+    std::vector<Dev> dv(n_devices);
+    for (uint32_t k = 0; k < n_devices; ++k) {
+        dv[k].id = devices[k];
+        for (uint32_t j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail(B200RT_EINVAL, "device %d listed twice", devices[k]);
+    }
+    // phase 1, one host thread per device: scene upload (+ BVH build) and the render launch
+    auto work = [&](uint32_t k) {
+        Dev& d = dv[k];
+        auto bad = [&](int rc) { d.rc = rc; d.err = g_last_error; };
+        int dev = 0;
+        if (int rc = resolve_device(d.id, &dev)) return bad(rc);
+        if (cudaSetDevice(dev) != cudaSuccess) { fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", dev); return bad(B200RT_ECUDA); }
+        if (int rc = b200rt_scene_create(desc, dev, &d.scene)) return bad(rc);
+        cudaError_t e = cudaMalloc(&d.accum, px * sizeof(float4));
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) { fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, "device %d: %s", dev, cudaGetErrorString(e)); return bad(B200RT_ECUDA); }
+        B200rtRenderParams p = *prm;
+        const uint32_t s0 = (uint32_t)((uint64_t)total * k / n_devices), s1 = (uint32_t)((uint64_t)total * (k + 1) / n_devices);
+        p.flags &= ~B200RT_FLAG_ACCUMULATE; p.device = -1;
+        p.sample_offset = prm->sample_offset + s0; p.samples = s1 - s0;
+        if (s1 == s0) { if (cudaMemsetAsync(d.accum, 0, px * sizeof(float4), d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "memset failed"); return bad(B200RT_ECUDA); } }   // more devices than samples
+        else { if (int rc = b200rt_render_device(d.scene, cam, &p, d.accum, d.stream)) return bad(rc); d.ran = true; }
+        if (cudaEventRecord(d.done, d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "cudaEventRecord failed"); return bad(B200RT_ECUDA); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (uint32_t k = 1; k < n_devices; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    int rc = B200RT_OK;
+    for (auto& d : dv) if (d.rc && rc == B200RT_OK) { rc = d.rc; g_last_error = d.err; }
+    // phase 2 on the first device: wait for everyone, fused sum + resolve over peer access, copy the frame out
+    uint8_t* d_rgb = nullptr;
+    int dev0 = -1;
+    if (rc == B200RT_OK) rc = resolve_device(dv[0].id, &dev0);
+    if (rc == B200RT_OK) {
+        DeviceGuard guard(dev0);
+        for (uint32_t k = 1; k < n_devices && rc == B200RT_OK; ++k) {
+            int can = 0, devk = 0;
+            resolve_device(dv[k].id, &devk);
+            cudaDeviceCanAccessPeer(&can, dev0, devk);
+            if (!can) { rc = fail(B200RT_ECUDA, "device %d cannot access device %d's memory (no peer path)", dev0, devk); break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devk, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", devk, cudaGetErrorString(e));
+        }
+        if (rc == B200RT_OK && cudaMalloc(&d_rgb, px * 3) != cudaSuccess) rc = fail(B200RT_ENOMEM, "rgb8 buffer");
+        if (rc == B200RT_OK) {
+            const float* ptrs[MAX_PEERS];
+            for (uint32_t k = 0; k < n_devices; ++k) {
+                ptrs[k] = dv[k].accum;
+                if (k && cudaStreamWaitEvent(dv[0].stream, dv[k].done, 0) != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaStreamWaitEvent failed");
+            }
+            if (rc == B200RT_OK) rc = b200rt_resolve_peers_rgb8_device(ptrs, n_devices, cam->image_width, cam->image_height, total, 0, 0, d_rgb, dv[0].stream);
+            if (rc == B200RT_OK) {
+                cudaError_t e = cudaMemcpyAsync(out_rgb8, d_rgb, px * 3, cudaMemcpyDeviceToHost, dv[0].stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(dv[0].stream);
+                if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "frame copy-back: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    // statistics + teardown (every device is idle once device 0's stream has drained; on an error path drain each)
+    if (stats) memset(stats, 0, sizeof *stats);
+    for (auto& d : dv) {
+        int dev = 0;
+        if (resolve_device(d.id, &dev) != B200RT_OK) continue;
+        DeviceGuard guard(dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.ran) {
+            B200rtStats st{};
+            if (b200rt_render_device_finish(d.scene, d.stream, &st) == B200RT_OK && stats) {
+                stats->rays += st.rays; stats->paths += st.paths; stats->node_visits += st.node_visits; stats->prim_tests += st.prim_tests;
+                stats->depth_exhausted += st.depth_exhausted; stats->launches += st.launches;
+                stats->kernel_ms = std::max(stats->kernel_ms, st.kernel_ms); stats->total_ms = std::max(stats->total_ms, st.total_ms);
+            }
+        }
+        if (d.scene) b200rt_scene_destroy(d.scene);
+        if (d.accum) cudaFree(d.accum);
+        if (d.done) cudaEventDestroy(d.done);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (d_rgb && dev0 >= 0) { DeviceGuard guard(dev0); cudaFree(d_rgb); }
+    if (stats && rc == B200RT_OK) stats->launches += 1;
+    return rc;
 }
 
 int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream) {

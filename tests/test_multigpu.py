@@ -77,3 +77,26 @@ def test_two_gpu_peer_resolve_matches_one_gpu(tmp_path, rt, gpu_required, barrie
     assert np.array_equal(got["frame1"], want)
     assert not np.array_equal(got["frame0"], got["frame1"])      # different seeds, both assembled
     assert got["frame0"].std() > 10
+
+
+def test_single_process_multi_gpu_render(rt, gpu_required, tmp_path):
+    """b200rt_render_rgb8_multi: one process, the samples split over two devices, the sum fused into the resolve over
+    peer access — the same picture as one device rendering all the samples (f32 partial sums: +-1 level at most)."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    scene = rt.Scene.named("random", seed=0xDEADBEEF)
+    cam = rt.default_camera(240)
+    one, st1 = rt.render_scene(scene, cam, samples=9, max_reflect=50, output=None, seed=12)
+    two, st2 = rt.render_scene_multi(scene, cam, samples=9, max_reflect=50, devices=(0, 1), seed=12)
+    assert st2.rays == st1.rays and st2.paths == st1.paths           # the same (pixel, sample) streams, 4 + 5 per device
+    d = np.abs(one.astype(int) - two.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    solo, _ = rt.render_scene_multi(scene, cam, samples=9, devices=(1,), seed=12)   # a single, non-default device
+    assert np.array_equal(solo, one)
+    with pytest.raises(rt.B200rtError):
+        rt.render_scene_multi(scene, cam, samples=4, devices=(0, 0))
+    cli = os.path.join(ROOT, "ray-cli")
+    r = subprocess.run([cli, "-v", "render", "random", "--seed", "5", "-w", "120", "-s", "6", "--gpus", "2", "-o", str(tmp_path / "m.png")], capture_output=True, text=True)
+    assert r.returncode == 0 and "on 2 GPUs" in r.stderr, r.stderr
