@@ -53,6 +53,7 @@ int  oracle_tree_info(const OracleScene* s, uint64_t* n_nodes, uint64_t* max_dep
 int  oracle_closest_hit(const OracleScene* s, const B200rtRay* rays, size_t n, double t_min, double t_max,
                         int32_t* ids, OracleHit* hits, OracleMargin* margins, OracleStats* stats);
 /* f32 restatement of the device arithmetic over every object in id order (gpu_f32.hpp). */
+int  oracle_closest_hit_f64(const OracleScene* s, const double* rays6, size_t n, double t_min, double t_max, int32_t* ids, OracleHit* hits);
 int  oracle_closest_hit_gpu32(const B200rtSceneDesc* desc, const B200rtRay* rays, size_t n, float t_min, float t_max, B200rtHit* hits);
 
 /* MaterialType::scatter + emitted. Record i draws from stream (seed, i, 0) unless

@@ -218,6 +218,22 @@ int oracle_closest_hit(const OracleScene* s, const B200rtRay* rays, size_t n, do
     return closest_hit_impl<double>(*s->s64, s->s64.get(), rays, n, t_min, t_max, ids, hits, margins, stats);
 }
 
+// The same query with f64 rays (the reference's own precision, core/math.rs:5): what pins the restatement against
+// the reference's unit-test values exactly — a ray such as (0.9, 0.9, -1.5) is not representable in f32.
+int oracle_closest_hit_f64(const OracleScene* s, const double* rays6, size_t n, double t_min, double t_max, int32_t* ids, OracleHit* hits) {
+    if (!s || !s->s64 || (n && (!rays6 || !ids))) return -1;
+    std::vector<size_t> stack;
+    for (size_t i = 0; i < n; ++i) {
+        const double* r = rays6 + 6 * i;
+        Ray<double> ray{{r[0], r[1], r[2]}, {r[3], r[4], r[5]}};
+        HitRecord<double> rec;
+        long id = s->s64->hit(stack, ray, t_min, t_max, rec, nullptr);
+        ids[i] = (int32_t)id;
+        if (hits) { if (id >= 0) put_hit(rec, id, &hits[i]); else { std::memset(&hits[i], 0, sizeof(OracleHit)); hits[i].id = -1; } }
+    }
+    return 0;
+}
+
 int oracle_closest_hit_gpu32(const B200rtSceneDesc* desc, const B200rtRay* rays, size_t n, float t_min, float t_max, B200rtHit* hits) {
     if (!desc || (n && (!rays || !hits))) return -1;
 #pragma omp parallel for schedule(dynamic, 256)

@@ -35,6 +35,7 @@ def _load():
         "oracle_scene_destroy": (None, [vp]),
         "oracle_tree_info": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "oracle_closest_hit": (i32, [vp, vp, sz, dbl, dbl, vp, vp, vp, C.POINTER(OracleStats)]),
+        "oracle_closest_hit_f64": (i32, [vp, vp, sz, dbl, dbl, vp, vp]),
         "oracle_closest_hit_gpu32": (i32, [vp, vp, sz, C.c_float, C.c_float, vp]),
         "oracle_scatter": (i32, [vp, vp, vp, sz, u64, vp, sz, vp]),
         "oracle_camera_rays": (i32, [vp, i32, vp, sz, u64, vp]),
@@ -101,6 +102,16 @@ class OracleScene:
                                     mg.ctypes.data if margins else None, C.byref(st))
         assert rc == 0
         return ids, hits, mg, st
+
+    def closest_hit_f64(self, rays, t_min=0.001, t_max=float("inf")):
+        """Rays as f64 (the reference's precision): exact replay of the reference's unit-test values."""
+        r = np.ascontiguousarray(rays, dtype=np.float64)
+        assert r.ndim == 2 and r.shape[1] == 6
+        ids = np.empty(r.shape[0], dtype=np.int32)
+        hits = np.zeros(r.shape[0], dtype=HIT_DTYPE)
+        rc = lib.oracle_closest_hit_f64(self._h, r.ctypes.data, r.shape[0], t_min, t_max, ids.ctypes.data, hits.ctypes.data)
+        assert rc == 0
+        return ids, hits
 
     def scatter(self, rays, hits, seed=0, injected=None):
         r = _rays(rays)
