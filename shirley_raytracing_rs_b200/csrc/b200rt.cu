@@ -446,9 +446,11 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     std::vector<GeomRec> geom(d->n_prims);
     std::vector<MatRec> mats(d->n_prims);
     std::vector<BuildPrim> bprims;
-    bprims.reserve(d->n_prims);
+    std::vector<BuildPrim> bp_all(d->n_prims);       // one slot per primitive (code < 0: no leaf), compacted below
     float max_abs = 0.f;
-    for (uint32_t i = 0; i < d->n_prims; ++i) {
+#pragma omp parallel for schedule(static) reduction(max : max_abs) if (d->n_prims >= 65536)
+    for (long long ii = 0; ii < (long long)d->n_prims; ++ii) {
+        const uint32_t i = (uint32_t)ii;
         const B200rtPrimRef& p = d->prims[i];
         GeomRec g{}; HostBox b{};
         if (p.type == B200RT_PRIM_SPHERE) {
@@ -486,11 +488,13 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         // here they simply get no leaf.  NaN boxes likewise.
         bool valid = true;
         for (int k = 0; k < 3; ++k) valid = valid && (b.lo[k] <= b.hi[k]);
-        if (!valid) continue;
-        BuildPrim bp; bp.box = b; bp.code = (int)((p.type << B200RT_LEAF_TYPE_SHIFT) | i);
-        for (int k = 0; k < 3; ++k) { bp.centroid[k] = 0.5f * (b.lo[k] + b.hi[k]); max_abs = std::max(max_abs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))); }
-        bprims.push_back(bp);
+        BuildPrim bp; bp.box = b; bp.code = valid ? (int)((p.type << B200RT_LEAF_TYPE_SHIFT) | i) : -1;
+        for (int k = 0; k < 3; ++k) { bp.centroid[k] = 0.5f * (b.lo[k] + b.hi[k]); if (valid) max_abs = std::max(max_abs, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]))); }
+        bp_all[i] = bp;
     }
+    bprims.reserve(d->n_prims);
+    for (const BuildPrim& bp : bp_all) if (bp.code >= 0) bprims.push_back(bp);
+    std::vector<BuildPrim>().swap(bp_all);
     lap("flatten prims + materials");
     // Scene-spanning primitives leave the BVH for the up-front list (DeviceScene::top_prims):
     // a box whose surface area is >= 30 % of the whole scene's is met by nearly every ray.
