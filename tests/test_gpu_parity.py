@@ -457,3 +457,49 @@ def test_exact_slab_path_gives_the_same_hits(rt, po, weekend, gpu_required, monk
     far = rays[:2000].copy(); far[:, :3] += np.float32(3.0e5)
     ids_far, _, _ = rt.closest_hit(weekend, far, 0.001, INF)
     assert np.array_equal(ids_far, po.closest_hit_gpu32(weekend.desc, far, 0.001, INF)["id"])
+
+
+# ---- edge cases of the frame: ragged tiles, empty and one-object scenes, degenerate parameters ----------------
+def test_ragged_image_sizes_and_tiny_scenes(rt, po, gpu_required):
+    """Image sizes that are not multiples of the 8x4 warp tile (partially valid tiles, work list with < 32 pixels),
+    one-pixel images, an empty scene (pure sky, bvh/bbox_tree.rs:110-119) and a single object."""
+    empty = rt.SceneBuilder().finalize()
+    one = sphere_scene(rt, [((0, 0, 0), 1.0)])
+    weekend = rt.Scene.named("random", seed=2)
+    for (w, ratio) in ((37, (3, 2)), (9, (1, 1)), (1, (1, 1)), (130, (16, 9))):
+        cam = rt.default_camera(w, aspect_ratio=ratio)
+        W, H = cam.image_width, cam.image_height
+        for scene in (empty, one, weekend):
+            acc, st = rt.render(scene, cam, samples=6, seed=9)
+            assert acc.shape == (H, W, 4) and st.paths == W * H * 6 and np.all(acc[..., 3] == 6) and np.all(np.isfinite(acc))
+            again, _ = rt.render(scene, cam, samples=6, seed=9)
+            assert np.array_equal(acc, again)
+            if H > 1:                                                    # row ranges cut through tiles
+                k = H // 2
+                a, _ = rt.render(scene, cam, samples=6, seed=9, rows=(0, k))
+                b, _ = rt.render(scene, cam, samples=6, seed=9, rows=(k, H))
+                assert np.array_equal(a + b, acc)
+        # the empty scene is the sky gradient of skybox/mod.rs:5-9 for every sample: compare with the oracle's mean
+        acc, st = rt.render(empty, cam, samples=64, seed=1)
+        assert st.rays == st.paths
+        want, _ = po.OracleScene(empty.desc).render(cam, 64, seed=2)
+        np.testing.assert_allclose(acc[..., :3] / 64, want / 64, atol=2e-2 if W * H < 64 else 8e-3)
+        rgb = rt.resolve_rgb8(acc)
+        assert rgb.shape == (H, W, 3) and rgb[..., 2].min() >= 250       # sky: blue channel is 1.0 everywhere
+
+
+def test_degenerate_parameters(rt, gpu_required):
+    s = rt.Scene.named("random", seed=2)
+    cam = rt.default_camera(64)
+    a0, st0 = rt.render(s, cam, samples=0, seed=1)                        # samples 0 -> 1 (src/main.rs:75-80)
+    a1, st1 = rt.render(s, cam, samples=1, seed=1)
+    assert np.array_equal(a0, a1) and st0.paths == st1.paths == cam.image_width * cam.image_height
+    z, stz = rt.render(s, cam, samples=3, max_depth=0, seed=1)            # depth 0: ray_color's loop never runs, colour is black
+    assert np.all(z[..., :3] == 0) and stz.rays == 0
+    F = rt._ffi
+    with pytest.raises(rt.B200rtError):
+        rt.render(s, cam, samples=1, rows=(10, 5))
+    with pytest.raises(rt.B200rtError):
+        rt.render(s, cam, samples=1, rows=(0, cam.image_height + 1))
+    with pytest.raises(rt.B200rtError):
+        rt.render(s, cam, samples=1, shard=(2, 2))
