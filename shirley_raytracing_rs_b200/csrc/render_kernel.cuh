@@ -103,17 +103,24 @@ __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v
 }
 
 // ------------------------------------------------------------------------------------------
-// K2 (v2): the same persistent kernel restructured for SIMT efficiency (ncu on v1: 8.1 of 32
-// lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble
-// texture at 2.7):
-//  * while-while traversal: every lane runs inner-node visits until it holds a leaf, then the
-//    warp tests the postponed leaves together;
-//  * the traversal cursor is resumable, and the warp leaves the traversal loop as soon as
-//    fewer than `trav_threshold` lanes are still traversing: finished lanes shade, scatter and
-//    start their next segment (or next sample) instead of idling until the slowest lane ends;
-//  * scene-spanning primitives are tested up front, uniformly (DeviceScene::top_prims);
+// K2: the persistent path-tracing kernel (render_scanline + ray_color, render.rs:17-70).
+// Grid = one CTA of BLK threads per SM; every warp pulls 8x4-pixel tiles from a global counter (bottom rows
+// first: the geometry-heavy tiles are scheduled before the cheap sky tiles) and works through the tile's
+// (pixel, sample) list with all 32 lanes.  ncu on the first, straight-loop design (render_variants.cuh) showed
+// 8.1 of 32 lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble texture
+// at 2.7 — so this kernel is organised around lane utilisation and instruction count:
+//  * one outer iteration = shade the lanes whose traversal finished -> hand new paths to lanes without one
+//    (from a per-warp ring of primary rays generated 32 at a time) -> ONE shared per-segment set-up for both
+//    groups (IEEE reciprocals, scene-spanning primitives tested up front) -> traverse;
+//  * while-while traversal with a resumable cursor: every lane runs inner-node visits until it holds a leaf,
+//    the warp tests the postponed leaves together, and leaves the loop as soon as fewer than `trav_threshold`
+//    lanes still traverse (finished lanes never idle until the slowest lane ends);
+//  * the inner-node visit is branch-free: three-FMA slab tests on centre/half-extent boxes (FAST; the exact
+//    Aabb::hit2 arithmetic otherwise), predicates feeding one predicated push / pop on a sentinel stack;
 //  * the Perlin marble is evaluated by the whole warp (coop_turbulence);
-//  * one-FMA slab planes against padded boxes (FAST).
+//  * per-pixel sums are 64-bit fixed-point shared-memory atomics: the image is bit-deterministic and independent
+//    of scheduling, row ranges, tile shards and sample ranges.
+// DESIGN.md §3 has the measurements behind each of these.
 // ------------------------------------------------------------------------------------------
 template <class Acc, bool COUNT, bool FAST, int BLK, int MINB>
 __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_constant__ RenderArgs a) {
