@@ -5,7 +5,7 @@ NVCC      ?= nvcc
 # the image exports CXX=/opt/gcc/bin/g++, which has no libgomp.spec; use the system compiler
 HOSTCXX   ?= /usr/bin/g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp -Xptxas -v --expt-relaxed-constexpr
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fopenmp -Xptxas -v --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 # make DEV=1: compile only the default render-kernel variant (fast iteration)
 ifdef DEV
 NVFLAGS   += -DB200RT_DEV_BUILD
