@@ -287,6 +287,12 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     int block_threads = env_int("B200RT_BLOCK", 768);
     if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
     if (kernel_version == 1) block_threads = BLOCK;
+#ifdef B200RT_DEV_BUILD
+#ifndef B200RT_DEV_BLK
+#define B200RT_DEV_BLK 768
+#endif
+    block_threads = B200RT_DEV_BLK;      // `make DEV=1 [EXTRA_NVFLAGS=-DB200RT_DEV_BLK=640]`: the one CTA size compiled
+#endif
     a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 8)));
     a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
     a.wf_fetch = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_FETCH", 8)));
@@ -342,8 +348,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
 #ifdef B200RT_DEV_BUILD
     // `make DEV=1`: only the default variant, for fast edit-compile-measure loops
     if (kernel_version != 2) return fail(B200RT_EINVAL, "dev build: only B200RT_KERNEL=2 is compiled");
-    block_threads = 768;
-#define B200RT_GO(ACC, CNT, FST) go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>)
+#define B200RT_GO(ACC, CNT, FST) go(path_trace_kernel_v2<ACC, CNT, FST, B200RT_DEV_BLK, 1>)
     if (plan.all_in_smem) {
         if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
         else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
