@@ -503,3 +503,30 @@ def test_degenerate_parameters(rt, gpu_required):
         rt.render(s, cam, samples=1, rows=(0, cam.image_height + 1))
     with pytest.raises(rt.B200rtError):
         rt.render(s, cam, samples=1, shard=(2, 2))
+
+
+def test_checker_on_a_coordinate_plane(rt, po, gpu_required):
+    """CheckerTexture::value (checker.rs:27-37) on a surface lying in a coordinate plane: sin(0) = 0 makes the
+    product +-0, which is not < 0, so the reference always takes `even` there — the floor-parity evaluation
+    must do the same (it special-cases an exactly zero argument)."""
+    b = rt.SceneBuilder()
+    tex = rt.TextureLoader.checker(5.0, rt.TextureLoader.solid(1, 0, 0), rt.TextureLoader.solid(0, 0, 1))   # odd red, even blue
+    b.add(rt.xz_rect(-5, 5, -5, 5, 0.0), rt.Lambertian(tex))
+    s = b.finalize()
+    d = s.desc.contents
+    t = d.materials[0].texture
+    rng = np.random.default_rng(3)
+    uvp = np.zeros((6000, 5), dtype=np.float32)
+    uvp[:, 2:] = rng.uniform(-5, 5, size=(6000, 3))
+    uvp[:2000, 3] = 0.0          # y = 0
+    uvp[2000:4000, 2] = 0.0      # x = 0
+    uvp[4000:, 4] = -0.0         # z = -0
+    got = rt.texture_value(s, t, uvp)
+    want = po.OracleScene(s.desc).texture_value(t, uvp.astype(np.float64))
+    assert np.array_equal(got, want.astype(np.float32))
+    assert np.all(got[:, 2] == 1.0) and np.all(got[:, 0] == 0.0)          # always `even` (blue)
+    # away from the planes both cells occur and the GPU agrees with the oracle except within rounding of a boundary
+    uvp[:, 2:] = rng.uniform(-5, 5, size=(6000, 3))
+    got = rt.texture_value(s, t, uvp)
+    want = po.OracleScene(s.desc).texture_value(t, uvp.astype(np.float64))
+    assert 0.3 < got[:, 0].mean() < 0.7 and (np.abs(got - want).max(axis=1) > 0).mean() < 1e-3
