@@ -195,7 +195,6 @@ __global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
     GmemAcc acc;
     acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
     acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
-    acc.top = nullptr; acc.n_top = 0;
     B200rtRay in{}; B200rtHit hi{}; hi.id = -1;
     if (in_range) { in = a.rays[i]; hi = a.hits[i]; }
     B200rtScatter out; memset(&out, 0, sizeof out);
@@ -250,7 +249,6 @@ __global__ void texture_value_kernel(const __grid_constant__ TexArgs a) {
     GmemAcc acc;
     acc.nodes = reinterpret_cast<const float4*>(a.scene.nodes); acc.geom = reinterpret_cast<const float4*>(a.scene.geom);
     acc.mats = reinterpret_cast<const float4*>(a.scene.mats); acc.tex = reinterpret_cast<const float4*>(a.scene.tex);
-    acc.top = nullptr; acc.n_top = 0;
     const float* q = a.uvp5 + (in_range ? i : 0) * 5;
     HitRec h;
     h.id = -1; h.type = 0xffu; h.face = 0; h.t = 0; h.front = true;

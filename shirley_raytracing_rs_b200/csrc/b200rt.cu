@@ -165,7 +165,7 @@ int validate(const B200rtSceneDesc* d) {
     return B200RT_OK;
 }
 
-// shared-memory budget: stage everything when it fits, else the top of the BVH
+// shared-memory budget: stage the whole scene when it fits, else nothing (the L1 cache does better)
 SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target, uint32_t block_threads = BLOCK, size_t extra_bytes = 0) {
     SmemPlan p{};
     const DeviceScene& s = sc->ds;
@@ -180,16 +180,11 @@ SmemPlan make_plan(const B200rtScene* sc, uint32_t blocks_per_sm_target, uint32_
         p.all_in_smem = 1; p.n_top = s.n_nodes;
         p.bytes = (uint32_t)(scene_bytes + stack_bytes);
     } else {
-        size_t room = budget > stack_bytes ? budget - stack_bytes : 0;
-        // Shared memory left unused is L1 cache for everything read from global memory, and the
-        // hardware cache beats a large staged prefix: 1e6-sphere scene 6.4 -> 7.3 Grays/s, 1e5-sphere
-        // 7.5 -> 9.0 with 8 KB (the top 7 levels) staged instead of ~90 KB (B200RT_TOP_KB to vary).
-        size_t top_kb = 8;
-        if (const char* v = getenv("B200RT_TOP_KB")) top_kb = (size_t)std::max(0, atoi(v));
-        room = std::min(room, top_kb * 1024);
+        // Scenes that do not fit: nothing is staged, every array is read through __ldg and the shared memory
+        // left over is L1 cache (a staged prefix of the tree was measured slower — rt_device.cuh: GmemAcc).
         p.all_in_smem = 0;
-        p.n_top = (uint32_t)std::min<size_t>(s.n_nodes, room / 64);
-        p.bytes = (uint32_t)((size_t)p.n_top * 64 + stack_bytes);
+        p.n_top = 0;
+        p.bytes = (uint32_t)stack_bytes;
     }
     return p;
 }

@@ -74,15 +74,10 @@ template <> struct Stager<SmemAcc> {
 };
 template <> struct Stager<GmemAcc> {
     static __device__ __forceinline__ GmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
-        uint32_t n_top4 = plan.n_top * 4;
-        const float4* gn = reinterpret_cast<const float4*>(s.nodes);
-        for (uint32_t i = threadIdx.x; i < n_top4; i += blockDim.x) smem[i] = __ldg(gn + i);
-        *stack = reinterpret_cast<int*>(smem + n_top4);
-        __syncthreads();
+        *stack = reinterpret_cast<int*>(smem);     // nothing staged: shared memory holds only the per-CTA working arrays
         GmemAcc a;
-        a.nodes = gn; a.geom = reinterpret_cast<const float4*>(s.geom);
+        a.nodes = reinterpret_cast<const float4*>(s.nodes); a.geom = reinterpret_cast<const float4*>(s.geom);
         a.mats = reinterpret_cast<const float4*>(s.mats); a.tex = reinterpret_cast<const float4*>(s.tex);
-        a.top = smem; a.n_top = (int)plan.n_top;
         return a;
     }
 };
