@@ -30,9 +30,17 @@ cli: ray-cli
 ray-cli: $(PKG)/cli/ray_cli.cpp $(LIB) $(HOST_HDRS)
 	$(HOSTCXX) $(CXXFLAGS) -o $@ $< -L$(PKG) -lb200rt -Wl,-rpath,'$$ORIGIN/$(PKG)'
 
-build/b200rt.o: $(CSRC)/b200rt.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/bvh_build.hpp include/b200rt.h
+# The build mode (full / DEV) is recorded in build/.mode, rewritten only when it changes, and is a prerequisite of
+# the CUDA object: switching between `make DEV=1` and `make` always recompiles, so a stale DEV library never ships.
+MODE := $(if $(DEV),dev,full) $(EXTRA_NVFLAGS)
+build/.mode: FORCE
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/ptxas_b200rt.log || (cat build/ptxas_b200rt.log; false)
+	@if [ "$$(cat $@ 2>/dev/null)" != "$(MODE)" ]; then echo "$(MODE)" > $@; fi
+FORCE:
+
+build/b200rt.o: build/.mode $(CSRC)/b200rt.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/bvh_build.hpp include/b200rt.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/b200rt.cu -o $@ 2> build/ptxas_b200rt.log || (cat build/ptxas_b200rt.log; false)
 	@grep -E "error|warning: .*spill|bytes spill" build/ptxas_b200rt.log | grep -v "0 bytes spill" | head -20 || true
 
 build/png_writer.o: $(CSRC)/png_writer.cpp include/b200rt.h
@@ -55,4 +63,4 @@ $(ORACLE): oracle/oracle_capi.cpp oracle/oracle.hpp oracle/gpu_f32.hpp oracle/or
 clean:
 	rm -rf build $(LIB) $(ORACLE) ray-cli
 
-.PHONY: all lib oracle cli clean
+.PHONY: all lib oracle cli clean FORCE
