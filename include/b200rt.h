@@ -240,10 +240,19 @@ int  b200rt_render_rgb8(const B200rtScene* scene, const B200rtCamera* camera,
                         B200rtStats* stats);
 
 /* render_scene on SEVERAL GPUs from one host process: `params->samples` is the total per pixel, split into
- * contiguous sample ranges over `devices[0 .. n_devices)` (each gets its own copy of the scene, created by its
+ * contiguous sample ranges over `devices[0 .. n_devices)` (each gets its own copy of the scene, uploaded by its
  * own host thread); devices[0] sums the per-device buffers inside the resolve through peer access and returns
  * the RGB8 frame.  The devices must be peer-accessible (NVLink / NVSwitch box).  `stats` sums rays / paths and
- * takes the maximum of the kernel times. */
+ * takes the maximum of the kernel times.
+ * B200rtMulti is the frame-loop form: the handle owns what does not change between frames — one worker thread,
+ * stream, event and accumulation buffer per device, the frame buffer, peer access — so a frame costs only the
+ * scene upload, the launches and the copy-back.  b200rt_render_rgb8_multi is the one-shot form: it keeps one
+ * handle per device list for the life of the process. */
+typedef struct B200rtMulti B200rtMulti;
+int  b200rt_multi_create(const int* devices, uint32_t n_devices, B200rtMulti** out);
+int  b200rt_multi_render_rgb8(B200rtMulti* multi, const B200rtSceneDesc* desc, const B200rtCamera* camera,
+                              const B200rtRenderParams* params, uint8_t* out_rgb8, B200rtStats* stats);
+void b200rt_multi_destroy(B200rtMulti* multi);
 int  b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, uint32_t n_devices,
                               const B200rtCamera* camera, const B200rtRenderParams* params,
                               uint8_t* out_rgb8, B200rtStats* stats);
@@ -287,17 +296,19 @@ int  b200rt_peer_buffer_destroy(int device, void* d_ptr);    /* a pointer from _
  * slot 0: "my accumulation buffer is complete" (before the fused resolve), slot 1: "I have finished reading"
  * (before the next frame overwrites the buffers, and before rank 0 reads the assembled frame).  A peer that
  * never arrives ends the wait after timeout_ms (0 = 10 s) and is reported by b200rt_peer_timed_out
- * (*out = 1 + rank, 0 = none) instead of hanging the device. */
+ * (*out = 1 + rank, 0 = none) instead of hanging the device; the host must treat that frame as failed. */
 #define B200RT_PEER_FLAG_BYTES 256
 int  b200rt_peer_signal_device(uint32_t* const* d_flag_arrays, uint32_t n_peers, uint32_t my_rank,
                                uint32_t slot, uint32_t epoch, void* cuda_stream);
 int  b200rt_peer_wait_device(uint32_t* d_my_flags, uint32_t n_peers, uint32_t slot, uint32_t epoch,
                              uint32_t timeout_ms, void* cuda_stream);
-int  b200rt_peer_timed_out(const uint32_t* d_my_flags, uint32_t* out);
+int  b200rt_peer_timed_out(uint32_t* d_my_flags, uint32_t* out);   /* synchronises; reading a time-out also clears it */
+/* d_my_flags: this rank's flag array (or NULL).  When given, a resolve enqueued after a flag wait that timed out
+ * stores NOTHING (an incomplete peer buffer never becomes a frame); b200rt_peer_timed_out then reports the rank. */
 int  b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers,
                                       uint32_t width, uint32_t height, uint32_t samples,
                                       uint32_t row_begin, uint32_t row_end,
-                                      uint8_t* d_out_rgb8, void* cuda_stream);
+                                      uint8_t* d_out_rgb8, const uint32_t* d_my_flags, void* cuda_stream);
 
 /* Replaces RgbImage::save_with_format(.., Png) (image.rs:42): 8-bit RGB PNG via zlib. */
 int  b200rt_write_png(const char* path, const uint8_t* rgb8, uint32_t width, uint32_t height);

@@ -136,7 +136,10 @@ SIGNATURES = {
     "b200rt_peer_wait_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "b200rt_peer_timed_out": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "b200rt_resolve_peers_rgb8_device": (C.c_int, [_P(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                                   C.c_void_p, C.c_void_p]),
+                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200rt_multi_create": (C.c_int, [_P(C.c_int), C.c_uint32, _P(C.c_void_p)]),
+    "b200rt_multi_render_rgb8": (C.c_int, [C.c_void_p, _P(SceneDesc), _P(Camera), _P(RenderParams), C.c_void_p, _P(Stats)]),
+    "b200rt_multi_destroy": (None, [C.c_void_p]),
     "b200rt_write_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "b200rt_encode_png": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_void_p), _P(C.c_size_t)]),
     "b200rt_free": (None, [C.c_void_p]),

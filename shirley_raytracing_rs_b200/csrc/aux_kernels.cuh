@@ -108,6 +108,7 @@ struct PeerResolveArgs {
     const float4* accum[MAX_PEERS];
     uint32_t n_peers, W, H, samples, row_begin, row_end;
     uint8_t* out;
+    const uint32_t* abort_flag;     // non-zero (a flag wait timed out: some peer's buffer is not complete) -> store nothing
 };
 __device__ __forceinline__ float4 peer_sum(const PeerResolveArgs& a, size_t idx) {
     float4 c = __ldcg(a.accum[0] + idx);        // .cg: peer data must not be served from a stale L1 line
@@ -120,6 +121,7 @@ __device__ __forceinline__ float4 peer_sum(const PeerResolveArgs& a, size_t idx)
 __global__ void resolve_peers_kernel(const __grid_constant__ PeerResolveArgs a) {
     const uint32_t j = a.row_begin + blockIdx.y;
     if (j >= a.row_end) return;
+    if (a.abort_flag && *reinterpret_cast<const volatile uint32_t*>(a.abort_flag) != 0u) return;   // never resolve an incomplete frame
     const uint32_t groups = (a.W + 3) / 4;
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
@@ -168,7 +170,9 @@ __global__ void peer_wait_kernel(const uint32_t* my_flags, uint32_t n_peers, uin
         uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
         if ((int32_t)(v - epoch) >= 0) break;
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > timeout_ns) { atomicExch(timed_out, 1u + r); break; }   // a missing peer must not hang the GPU: report and go on
+        // a missing peer must not hang the GPU: record it (the fused resolve that follows sees the word and stores
+        // nothing; the host reads it with b200rt_peer_timed_out and fails the frame) and let the stream go on
+        if (t1 - t0 > timeout_ns) { atomicExch(timed_out, 1u + r); __threadfence(); break; }
         __nanosleep(200);
     }
 }

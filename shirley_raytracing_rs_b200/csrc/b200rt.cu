@@ -3,7 +3,6 @@
 // Device code (SURVEY.md §2 "new kernels") lives in the headers this file includes:
 //   rt_device.cuh        data layout, math, RNG, intersection, traversal steps, shading, textures
 //   render_kernel.cuh    K2 path_trace_kernel_v2   render_scanline + ray_color     (render.rs:17-70)
-//   render_variants.cuh  K2 design experiments v1 / v3, selectable with B200RT_KERNEL
 //   aux_kernels.cuh      K1 closest_hit_kernel     BboxTree::hit_workspace batch   (bvh/bbox_tree.rs:56-91)
 //                        K3 resolve_kernel (+ resolve_peers_kernel, flag barrier)  (image.rs:34-40, core/color.rs:31-38)
 //                        K4 scatter / camera_rays / texture_value / aabb_hit / rng parity hooks, FFMA-chain microbenchmark
@@ -14,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,7 +51,6 @@ static int fail(int code, const char* fmt, ...) {
 }  // namespace b200rt
 
 #include "render_kernel.cuh"
-#include "render_variants.cuh"
 #include "aux_kernels.cuh"
 
 
@@ -113,9 +112,6 @@ int resolve_device(int device, int* out) {
     return B200RT_OK;
 }
 
-// Scene arrays are packed into ONE pinned staging buffer and uploaded with ONE copy into ONE
-// device arena (256-byte aligned sub-allocations): a frame that re-creates its scene pays one
-// cudaMalloc + one H2D copy.
 // Layout of the one device allocation that holds every scene array.  Only offsets are assigned here;
 // each array is copied straight from where it lies on the host (a host-side staging copy of a
 // 1e6-sphere scene — 208 MB, grown piecewise — took 230 ms of scene_create's 360).
@@ -276,12 +272,10 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     bool count = (prm->flags & B200RT_FLAG_COUNT_TRAVERSAL) != 0;
 
     // Tunables (defaults are the measured best; env vars exist for A/B runs under ncu):
-    //   B200RT_KERNEL=1|2   B200RT_BLOCK=256|512|1024   B200RT_TRAV_THRESHOLD=1..32   B200RT_FAST_SLAB=0|1
+    //   B200RT_BLOCK=256|512|768   B200RT_TRAV_THRESHOLD=1..32   B200RT_FAST_SLAB=0|1
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
-    int kernel_version = env_int("B200RT_KERNEL", 2);
     int block_threads = env_int("B200RT_BLOCK", 768);
-    if (block_threads != 256 && block_threads != 512 && block_threads != 768 && block_threads != 1024) block_threads = 768;
-    if (kernel_version == 1) block_threads = BLOCK;
+    if (block_threads != 256 && block_threads != 512 && block_threads != 768) block_threads = 768;
 #ifdef B200RT_DEV_BUILD
 #ifndef B200RT_DEV_BLK
 #define B200RT_DEV_BLK 768
@@ -289,30 +283,21 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     block_threads = B200RT_DEV_BLK;      // `make DEV=1 [EXTRA_NVFLAGS=-DB200RT_DEV_BLK=640]`: the one CTA size compiled
 #endif
     a.trav_threshold = (uint32_t)std::min(32, std::max(1, env_int("B200RT_TRAV_THRESHOLD", 8)));
-    a.wf_inner = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_INNER", 12)));
-    a.wf_fetch = (uint32_t)std::min(32, std::max(1, env_int("B200RT_WF_FETCH", 8)));
-    a.wf_park = (uint32_t)std::min(33, std::max(0, env_int("B200RT_WF_PARK", 33)));
-    int pool_slots = env_int("B200RT_WF_POOL", 96);
-    if (pool_slots != 64 && pool_slots != 96 && pool_slots != 128) pool_slots = 96;
-    if (kernel_version == 3 && (block_threads != 256 || !getenv("B200RT_BLOCK"))) block_threads = 512;
-    // one-FMA slab planes are conservative only while |origin| * eps stays below the box padding
+    // the centre-form slab planes are conservative only while |origin| * eps stays below the box padding
     float max_origin = std::max(sc->max_abs_coord, std::max(std::fabs((float)cam->origin[0]), std::max(std::fabs((float)cam->origin[1]), std::fabs((float)cam->origin[2]))));
     bool fast_ok = sc->box_pad >= 4.0f * 1.1920929e-7f * max_origin;
     bool fast = fast_ok && env_int("B200RT_FAST_SLAB", 1) != 0;
 
-    uint32_t target_blocks = (block_threads == 256 && kernel_version != 3) ? 2 : 1;
-    size_t extra = kernel_version == 3 ? (size_t)(block_threads / 32) * pool_words(pool_slots) * 4
-                   : (kernel_version == 2 ? (size_t)(block_threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)) : 0);
-    SmemPlan plan = make_plan(sc, target_blocks, block_threads, extra);
-    if (!plan.all_in_smem && target_blocks > 1) { SmemPlan p1 = make_plan(sc, 1, block_threads, extra); if (p1.all_in_smem) plan = p1; }
+    auto extra_for = [](int threads) { return (size_t)(threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)); };
+    SmemPlan plan = make_plan(sc, 1, block_threads, extra_for(block_threads));
 #ifndef B200RT_DEV_BUILD
     // A deep tree (the device-built linear BVH can reach 40-50 levels) needs more stack per thread than
-    // 768 threads leave room for: fall back to smaller CTAs rather than fail.
-    while (kernel_version == 2 && plan.bytes + 1024 > sc->smem_optin && block_threads > 256) {
+    // 768 threads leave room for: fall back to smaller CTAs rather than fail.  (Only scenes that live in
+    // global memory get that deep; a scene that fits in shared memory always runs 768-thread CTAs.)
+    if (plan.all_in_smem) block_threads = 768, plan = make_plan(sc, 1, 768, extra_for(768));
+    while (!plan.all_in_smem && plan.bytes + 1024 > sc->smem_optin && block_threads > 256) {
         block_threads = block_threads > 512 ? 512 : 256;
-        target_blocks = 1;
-        extra = (size_t)(block_threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t));
-        plan = make_plan(sc, target_blocks, block_threads, extra);
+        plan = make_plan(sc, 1, block_threads, extra_for(block_threads));
     }
 #endif
     a.plan = plan;
@@ -320,7 +305,10 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     scr->launches = 0;
     CU(cudaEventRecord(scr->ev0, stream));
     CU(cudaMemsetAsync(scr->d_counters, 0, sizeof(Counters), stream));
-    if (!a.accumulate) CU(cudaMemsetAsync(d_accum, 0, (size_t)W * H * sizeof(float4), stream));
+    // The kernel stores every pixel of the tiles it renders; the buffer is cleared only when some pixels are outside them
+    // ("pixels outside the selected rows/tiles are written as zeros", include/b200rt.h).
+    const bool covers_frame = a.shard_count == 1 && a.row_begin == 0 && a.row_end == H;
+    if (!a.accumulate && !covers_frame) CU(cudaMemsetAsync(d_accum, 0, (size_t)W * H * sizeof(float4), stream));
     int blocks_per_sm = 0;
     auto go = [&](auto kernel) -> int {
         int rc = set_smem(kernel, plan.bytes); if (rc) return rc;
@@ -339,54 +327,18 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         return B200RT_OK;
     };
     int rc;
-    if (kernel_version == 2 && fast) a.scene.nodes = sc->ds.cnodes;   // centre/half-extent boxes for aabb_center
+    // Instantiations shipped: {fast, fast + counters, exact + counters} per accessor and CTA size (the exact-slab
+    // fallback always counts: it is the rare path and one variant fewer to compile).
 #ifdef B200RT_DEV_BUILD
-    // `make DEV=1`: only the default variant, for fast edit-compile-measure loops
-    if (kernel_version != 2) return fail(B200RT_EINVAL, "dev build: only B200RT_KERNEL=2 is compiled");
 #define B200RT_GO(ACC, CNT, FST) go(path_trace_kernel_v2<ACC, CNT, FST, B200RT_DEV_BLK, 1>)
-    if (plan.all_in_smem) {
-        if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
-        else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
-    } else {
-        if (count) rc = fast ? B200RT_GO(GmemAcc, true, true) : B200RT_GO(GmemAcc, true, false);
-        else rc = fast ? B200RT_GO(GmemAcc, false, true) : B200RT_GO(GmemAcc, false, false);
-    }
+    if (plan.all_in_smem) rc = !fast ? B200RT_GO(SmemAcc, true, false) : (count ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, false, true));
+    else rc = !fast ? B200RT_GO(GmemAcc, true, false) : (count ? B200RT_GO(GmemAcc, true, true) : B200RT_GO(GmemAcc, false, true));
 #undef B200RT_GO
 #else
-    if (kernel_version == 3) {
-#define B200RT_GO3(ACC, CNT, FST)                                                                            \
-        (block_threads == 256 ? (pool_slots == 64 ? go(path_trace_kernel_v3<ACC, CNT, FST, 256, 64>)         \
-                                 : pool_slots == 96 ? go(path_trace_kernel_v3<ACC, CNT, FST, 256, 96>)       \
-                                                    : go(path_trace_kernel_v3<ACC, CNT, FST, 256, 128>))     \
-                              : (pool_slots == 64 ? go(path_trace_kernel_v3<ACC, CNT, FST, 512, 64>)         \
-                                 : pool_slots == 96 ? go(path_trace_kernel_v3<ACC, CNT, FST, 512, 96>)       \
-                                                    : go(path_trace_kernel_v3<ACC, CNT, FST, 512, 128>)))
-        if (plan.all_in_smem) {
-            if (count) rc = fast ? B200RT_GO3(SmemAcc, true, true) : B200RT_GO3(SmemAcc, true, false);
-            else rc = fast ? B200RT_GO3(SmemAcc, false, true) : B200RT_GO3(SmemAcc, false, false);
-        } else {
-            if (count) rc = fast ? B200RT_GO3(GmemAcc, true, true) : B200RT_GO3(GmemAcc, true, false);
-            else rc = fast ? B200RT_GO3(GmemAcc, false, true) : B200RT_GO3(GmemAcc, false, false);
-        }
-#undef B200RT_GO3
-    } else if (kernel_version == 1) {
-        if (plan.all_in_smem) rc = count ? go(path_trace_kernel<SmemAcc, true>) : go(path_trace_kernel<SmemAcc, false>);
-        else rc = count ? go(path_trace_kernel<GmemAcc, true>) : go(path_trace_kernel<GmemAcc, false>);
-    } else {
-#define B200RT_GO(ACC, CNT, FST)                                                                             \
-        (block_threads == 256 ? go(path_trace_kernel_v2<ACC, CNT, FST, 256, 2>)                              \
-         : block_threads == 512 ? go(path_trace_kernel_v2<ACC, CNT, FST, 512, 1>)                            \
-         : block_threads == 1024 ? go(path_trace_kernel_v2<ACC, CNT, FST, 1024, 1>)                          \
-                                : go(path_trace_kernel_v2<ACC, CNT, FST, 768, 1>))
-        if (plan.all_in_smem) {
-            if (count) rc = fast ? B200RT_GO(SmemAcc, true, true) : B200RT_GO(SmemAcc, true, false);
-            else rc = fast ? B200RT_GO(SmemAcc, false, true) : B200RT_GO(SmemAcc, false, false);
-        } else {
-            if (count) rc = fast ? B200RT_GO(GmemAcc, true, true) : B200RT_GO(GmemAcc, true, false);
-            else rc = fast ? B200RT_GO(GmemAcc, false, true) : B200RT_GO(GmemAcc, false, false);
-        }
+#define B200RT_GO(ACC, BLK) (!fast ? go(path_trace_kernel_v2<ACC, true, false, BLK, 1>) : (count ? go(path_trace_kernel_v2<ACC, true, true, BLK, 1>) : go(path_trace_kernel_v2<ACC, false, true, BLK, 1>)))
+    if (plan.all_in_smem) rc = B200RT_GO(SmemAcc, 768);
+    else rc = block_threads == 256 ? B200RT_GO(GmemAcc, 256) : (block_threads == 512 ? B200RT_GO(GmemAcc, 512) : B200RT_GO(GmemAcc, 768));
 #undef B200RT_GO
-    }
 #endif
     if (rc) return rc;
     CU(cudaMemcpyAsync(scr->h_counters, scr->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
@@ -415,7 +367,7 @@ extern "C" {
 
 int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream);
 int b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers, uint32_t W, uint32_t H, uint32_t samples,
-                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, void* cuda_stream);
+                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, const uint32_t* d_my_flags, void* cuda_stream);
 
 const char* b200rt_last_error(void) { return g_last_error.c_str(); }
 int b200rt_abi_version(void) { return B200RT_ABI_VERSION; }
@@ -534,7 +486,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
         auto t0 = std::chrono::steady_clock::now();
         bvh = build_bvh(std::move(bprims));
         host_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (bvh.depth > 60) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
+        if (bvh.depth > BVH_MAX_DEPTH) return fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth);
     }
 
     lap(use_lbvh ? "top list + padding" : "top list + padding + host SAH");
@@ -557,37 +509,39 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     }
 
     static_assert(sizeof(HostNode) == sizeof(BvhNode), "node layout");
-    std::vector<BvhNode> nodes(bvh.nodes.size());
-    memcpy(nodes.data(), bvh.nodes.data(), nodes.size() * sizeof(BvhNode));
-    // The render kernel's copy of the tree: the same nodes with each child box as centre +
-    // half-extent (rt_device.cuh: aabb_center).  The box is re-derived outwards: c = (lo+hi)/2,
-    // h = max(hi - c, c - lo) bumped up one ulp, so [c - h, c + h] contains [lo, hi].  An empty
-    // child (lo > hi) gets h = -1: near > far on every axis, never entered.
-    const size_t n_nodes = use_lbvh ? lbvh_prims.size() - 1 : nodes.size();
-    std::vector<BvhNode> cnodes(nodes.size());
-#pragma omp parallel for schedule(static) if (nodes.size() >= 65536)
-    for (long long i = 0; i < (long long)nodes.size(); ++i) {
-        const float* q = reinterpret_cast<const float*>(&nodes[i]);
-        float* o = reinterpret_cast<float*>(&cnodes[i]);
-        for (int ch = 0; ch < 2; ++ch) {
-            const float* lo = q + 6 * ch; const float* hi = lo + 3;
-            for (int k = 0; k < 3; ++k) {
-                float c = 0.f, h = -1.f;
-                if (lo[k] <= hi[k]) {
-                    c = 0.5f * lo[k] + 0.5f * hi[k];
-                    h = std::nextafterf(std::max(hi[k] - c, c - lo[k]), INFINITY);
-                    if (!std::isfinite(c) || !std::isfinite(h)) { c = 0.f; h = 3.0e38f; }   // unbounded box: always entered
+    // The device's copy of the tree: each child box as centre + half-extent (rt_device.cuh: aabb_center),
+    // re-derived outwards from the builder's (lo, hi): c = (lo+hi)/2, h = max(hi - c, c - lo) bumped up one ulp,
+    // so [c - h, c + h] contains [lo, hi].  An empty child (lo > hi) gets h = -1: near > far on every axis, never
+    // entered.  ONE copy is uploaded; the exact-slab fallback derives (c - h, c + h) on the fly.
+    auto centre_form = [](const std::vector<HostNode>& src) {
+        std::vector<BvhNode> out(src.size());
+#pragma omp parallel for schedule(static) if (src.size() >= 65536)
+        for (long long i = 0; i < (long long)src.size(); ++i) {
+            const float* q = reinterpret_cast<const float*>(&src[i]);
+            float* o = reinterpret_cast<float*>(&out[i]);
+            for (int ch = 0; ch < 2; ++ch) {
+                const float* lo = q + 6 * ch; const float* hi = lo + 3;
+                for (int k = 0; k < 3; ++k) {
+                    float c = 0.f, h = -1.f;
+                    if (lo[k] <= hi[k]) {
+                        c = 0.5f * lo[k] + 0.5f * hi[k];
+                        h = std::nextafterf(std::max(hi[k] - c, c - lo[k]), INFINITY);
+                        if (!std::isfinite(c) || !std::isfinite(h)) { c = 0.f; h = 3.0e38f; }   // unbounded box: always entered
+                    }
+                    o[6 * ch + k] = c; o[6 * ch + 3 + k] = h;
                 }
-                o[6 * ch + k] = c; o[6 * ch + 3 + k] = h;
             }
+            o[12] = q[12]; o[13] = q[13]; o[14] = q[14]; o[15] = q[15];
         }
-        o[12] = q[12]; o[13] = q[13]; o[14] = q[14]; o[15] = q[15];
-    }
+        return out;
+    };
+    const size_t n_nodes = use_lbvh ? lbvh_prims.size() - 1 : bvh.nodes.size();
+    std::vector<BvhNode> cnodes;
+    if (!use_lbvh) cnodes = centre_form(bvh.nodes);
     lap("centre/half-extent nodes");
     Arena arena;
-    size_t off_nodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(nodes);
+    size_t off_nodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(cnodes);
     size_t off_geom = arena.put(geom), off_mats = arena.put(mats), off_tex = arena.put(tex);
-    size_t off_cnodes = use_lbvh ? arena.reserve(n_nodes * sizeof(BvhNode)) : arena.put(cnodes);
     // images: RGB8 -> RGBA8 so a texel is one 4-byte load
     std::vector<ImageRec> images(d->n_images);
     std::vector<size_t> off_img(d->n_images);
@@ -620,15 +574,28 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     }
     lap("cudaMalloc + H2D");
     sc->ds.nodes = reinterpret_cast<const BvhNode*>(dbase + off_nodes);
-    sc->ds.cnodes = reinterpret_cast<const BvhNode*>(dbase + off_cnodes);
     if (use_lbvh) {
         uint32_t depth = 0; float ms = 0.f;
-        cudaError_t e = lbvh::build(lbvh_prims, lbvh_bounds, reinterpret_cast<BvhNode*>(dbase + off_nodes), reinterpret_cast<BvhNode*>(dbase + off_cnodes), &depth, &ms);
+        cudaError_t e = lbvh::build(lbvh_prims, lbvh_bounds, reinterpret_cast<BvhNode*>(dbase + off_nodes), &depth, &ms);
         if (e != cudaSuccess) return bail(fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, "device BVH build: %s", cudaGetErrorString(e)));
-        if (depth > 60) return bail(fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack (B200RT_BUILDER=sah builds a shallower tree)", depth));
-        bvh.depth = depth;
         sc->info.bvh_build_ms = ms; sc->info.bvh_builder = 1;
         lap("device LBVH (incl. its uploads)");
+        const char* force = getenv("B200RT_LBVH_MAX_DEPTH");      // test hook: pretend the stack is shallower
+        const uint32_t limit = force && *force ? (uint32_t)atoi(force) : BVH_MAX_DEPTH;
+        if (depth > limit) {
+            // A linear BVH over strongly clustered primitives (many equal Morton prefixes) can be deeper than the
+            // traversal stack.  The host builder bounds its depth (median splits near the limit): rebuild with it into
+            // the same node slots (both builders emit n - 1 nodes) instead of failing.
+            auto t0 = std::chrono::steady_clock::now();
+            bvh = build_bvh(std::move(lbvh_prims));
+            host_build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (bvh.depth > BVH_MAX_DEPTH || bvh.nodes.size() != n_nodes) return bail(fail(B200RT_ESTACK, "BVH depth %u exceeds the traversal stack", bvh.depth));
+            cnodes = centre_form(bvh.nodes);
+            e = cudaMemcpy(dbase + off_nodes, cnodes.data(), n_nodes * sizeof(BvhNode), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return bail(fail(B200RT_ECUDA, "scene upload: %s", cudaGetErrorString(e)));
+            sc->info.bvh_build_ms = host_build_ms; sc->info.bvh_builder = 0;
+            lap("host SAH rebuild (device tree too deep)");
+        } else bvh.depth = depth;
     } else { sc->info.bvh_build_ms = host_build_ms; sc->info.bvh_builder = 0; }
     sc->ds.geom = reinterpret_cast<const GeomRec*>(dbase + off_geom);
     sc->ds.mats = reinterpret_cast<const MatRec*>(dbase + off_mats);
@@ -746,88 +713,181 @@ int b200rt_render_rgb8(const B200rtScene* csc, const B200rtCamera* cam, const B2
     return render_host_impl(csc, cam, prm, accum, out_rgb8, stats);
 }
 
-// render_scene on several GPUs from ONE host process (what a `ray-cli` user has): the scene is created on every
-// device by its own host thread, device k renders samples [k * S / N, (k + 1) * S / N) of every pixel into a buffer
-// of its own, and the first device resolves the frame with the fused sum (resolve_peers_kernel) reading the other
-// devices' buffers through peer access over NVLink.  One process per GPU + b200rt_peer_* is the other route.
-int b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, uint32_t n_devices, const B200rtCamera* cam,
-                             const B200rtRenderParams* prm, uint8_t* out_rgb8, B200rtStats* stats) {
-    if (!desc || !devices || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
+// ---- render_scene on several GPUs from ONE host process (what a `ray-cli` user has) -------------------------------
+// B200rtMulti keeps, for a fixed device list, everything a frame loop would otherwise re-create per call: one worker
+// thread, stream, completion event and accumulation buffer per device, the RGB8 frame buffer on the first device,
+// and peer access from the first device to the others (enabled once).  Per frame each worker uploads the scene to
+// its device (render_scene builds a new scene per call, src/main.rs:65-130) and launches the path tracer on its
+// sample range; the first device then waits on the others' events (stream-ordered, no host round trip), sums all
+// buffers inside the resolve (resolve_peers_kernel over NVLink peer pointers) and copies the frame out.
+}  // extern "C"
+
+struct B200rtMulti {
+    struct Dev {
+        int id = 0;
+        cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+        float* accum = nullptr; size_t accum_px = 0;
+        B200rtScene* scene = nullptr;
+        int rc = 0; std::string err; bool ran = false;
+        std::thread th;
+    };
+    std::vector<Dev> dv;
+    uint8_t* d_rgb = nullptr; size_t rgb_bytes = 0;
+    // one frame's job, published to the workers under `mu`
+    std::mutex mu; std::condition_variable cv_go, cv_done;
+    uint64_t generation = 0; uint32_t pending = 0; bool quit = false;
+    const B200rtSceneDesc* desc = nullptr; const B200rtCamera* cam = nullptr; const B200rtRenderParams* prm = nullptr;
+    std::mutex call_mu;            // one frame at a time per handle
+};
+
+namespace {
+
+// what device k does for a frame: scene upload (+ BVH build), buffer, launch on its sample range, completion event
+void multi_device_job(B200rtMulti* m, uint32_t k) {
+    B200rtMulti::Dev& d = m->dv[k];
+    d.rc = B200RT_OK; d.err.clear(); d.ran = false; d.scene = nullptr;
+    auto bad = [&](int rc) { d.rc = rc; d.err = g_last_error; };
+    if (cudaSetDevice(d.id) != cudaSuccess) { fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", d.id); return bad(B200RT_ECUDA); }
+    const uint32_t n = (uint32_t)m->dv.size();
+    const uint32_t total = m->prm->samples == 0 ? 1 : m->prm->samples;   // src/main.rs:75-80
+    const size_t px = (size_t)m->cam->image_width * m->cam->image_height;
+    if (int rc = b200rt_scene_create(m->desc, d.id, &d.scene)) return bad(rc);
+    if (d.accum_px < px) {
+        cudaFree(d.accum); d.accum = nullptr; d.accum_px = 0;
+        cudaError_t e = cudaMalloc(&d.accum, px * sizeof(float4));
+        if (e != cudaSuccess) { fail(B200RT_ENOMEM, "device %d: accumulation buffer: %s", d.id, cudaGetErrorString(e)); return bad(B200RT_ENOMEM); }
+        d.accum_px = px;
+    }
+    B200rtRenderParams p = *m->prm;
+    const uint32_t s0 = (uint32_t)((uint64_t)total * k / n), s1 = (uint32_t)((uint64_t)total * (k + 1) / n);
+    p.flags &= ~B200RT_FLAG_ACCUMULATE; p.device = -1;
+    p.sample_offset = m->prm->sample_offset + s0; p.samples = s1 - s0;
+    if (s1 == s0) {   // more devices than samples: this one contributes zeros
+        if (cudaMemsetAsync(d.accum, 0, px * sizeof(float4), d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "memset failed"); return bad(B200RT_ECUDA); }
+    } else {
+        if (int rc = b200rt_render_device(d.scene, m->cam, &p, d.accum, d.stream)) return bad(rc);
+        d.ran = true;
+    }
+    if (cudaEventRecord(d.done, d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "cudaEventRecord failed"); return bad(B200RT_ECUDA); }
+}
+
+void multi_worker(B200rtMulti* m, uint32_t k) {
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(m->mu);
+            m->cv_go.wait(lk, [&] { return m->quit || m->generation != seen; });
+            if (m->quit) return;
+            seen = m->generation;
+        }
+        multi_device_job(m, k);
+        { std::lock_guard<std::mutex> lk(m->mu); if (--m->pending == 0) m->cv_done.notify_all(); }
+    }
+}
+
+std::mutex g_multi_mu;
+std::map<std::vector<int>, B200rtMulti*> g_multi_cache;    // b200rt_render_rgb8_multi: one handle per device list, for the process
+
+}  // namespace
+
+extern "C" {
+
+void b200rt_multi_destroy(B200rtMulti* m) {
+    if (!m) return;
+    { std::lock_guard<std::mutex> lk(m->mu); m->quit = true; }
+    m->cv_go.notify_all();
+    for (auto& d : m->dv) if (d.th.joinable()) d.th.join();
+    for (auto& d : m->dv) {
+        DeviceGuard guard(d.id);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        if (d.accum) cudaFree(d.accum);
+        if (d.done) cudaEventDestroy(d.done);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (m->d_rgb && !m->dv.empty()) { DeviceGuard guard(m->dv[0].id); cudaFree(m->d_rgb); }
+    delete m;
+}
+
+int b200rt_multi_create(const int* devices, uint32_t n_devices, B200rtMulti** out) {
+    if (!devices || !out) return fail(B200RT_EINVAL, "NULL argument");
+    *out = nullptr;
     if (n_devices < 1 || n_devices > (uint32_t)MAX_PEERS) return fail(B200RT_EINVAL, "n_devices %u outside [1, %d]", n_devices, MAX_PEERS);
-    const uint32_t total = prm->samples == 0 ? 1 : prm->samples;   // src/main.rs:75-80
+    for (uint32_t k = 0; k < n_devices; ++k)
+        for (uint32_t j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail(B200RT_EINVAL, "device %d listed twice", devices[k]);
+    B200rtMulti* m = new B200rtMulti();
+    m->dv.resize(n_devices);
+    int rc = B200RT_OK;
+    for (uint32_t k = 0; k < n_devices && rc == B200RT_OK; ++k) {
+        B200rtMulti::Dev& d = m->dv[k];
+        if ((rc = resolve_device(devices[k], &d.id))) break;
+        DeviceGuard guard(d.id);
+        cudaError_t e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "device %d: %s", d.id, cudaGetErrorString(e));
+    }
+    if (rc == B200RT_OK && n_devices > 1) {     // the first device reads every other device's buffer in the fused resolve
+        DeviceGuard guard(m->dv[0].id);
+        for (uint32_t k = 1; k < n_devices && rc == B200RT_OK; ++k) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, m->dv[0].id, m->dv[k].id);
+            if (!can) { rc = fail(B200RT_ECUDA, "device %d cannot access device %d's memory (no peer path)", m->dv[0].id, m->dv[k].id); break; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(m->dv[k].id, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", m->dv[k].id, cudaGetErrorString(e));
+        }
+    }
+    if (rc != B200RT_OK) { std::string keep = g_last_error; b200rt_multi_destroy(m); g_last_error = keep; return rc; }
+    for (uint32_t k = 1; k < n_devices; ++k) m->dv[k].th = std::thread(multi_worker, m, k);
+    *out = m;
+    return B200RT_OK;
+}
+
+int b200rt_multi_render_rgb8(B200rtMulti* m, const B200rtSceneDesc* desc, const B200rtCamera* cam, const B200rtRenderParams* prm,
+                             uint8_t* out_rgb8, B200rtStats* stats) {
+    if (!m || !desc || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
     const size_t px = (size_t)cam->image_width * cam->image_height;
     if (px == 0) return fail(B200RT_EINVAL, "camera image dimensions are zero");
-    struct Dev { int id = 0; B200rtScene* scene = nullptr; float* accum = nullptr; cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; int rc = 0; std::string err; B200rtStats st{}; bool ran = false; };
-    std::vector<Dev> dv(n_devices);
-    for (uint32_t k = 0; k < n_devices; ++k) {
-        dv[k].id = devices[k];
-        for (uint32_t j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail(B200RT_EINVAL, "device %d listed twice", devices[k]);
-    }
-    // phase 1, one host thread per device: scene upload (+ BVH build) and the render launch
-    auto work = [&](uint32_t k) {
-        Dev& d = dv[k];
-        auto bad = [&](int rc) { d.rc = rc; d.err = g_last_error; };
-        int dev = 0;
-        if (int rc = resolve_device(d.id, &dev)) return bad(rc);
-        if (cudaSetDevice(dev) != cudaSuccess) { fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", dev); return bad(B200RT_ECUDA); }
-        if (int rc = b200rt_scene_create(desc, dev, &d.scene)) return bad(rc);
-        cudaError_t e = cudaMalloc(&d.accum, px * sizeof(float4));
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming);
-        if (e != cudaSuccess) { fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, "device %d: %s", dev, cudaGetErrorString(e)); return bad(B200RT_ECUDA); }
-        B200rtRenderParams p = *prm;
-        const uint32_t s0 = (uint32_t)((uint64_t)total * k / n_devices), s1 = (uint32_t)((uint64_t)total * (k + 1) / n_devices);
-        p.flags &= ~B200RT_FLAG_ACCUMULATE; p.device = -1;
-        p.sample_offset = prm->sample_offset + s0; p.samples = s1 - s0;
-        if (s1 == s0) { if (cudaMemsetAsync(d.accum, 0, px * sizeof(float4), d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "memset failed"); return bad(B200RT_ECUDA); } }   // more devices than samples
-        else { if (int rc = b200rt_render_device(d.scene, cam, &p, d.accum, d.stream)) return bad(rc); d.ran = true; }
-        if (cudaEventRecord(d.done, d.stream) != cudaSuccess) { fail(B200RT_ECUDA, "cudaEventRecord failed"); return bad(B200RT_ECUDA); }
-    };
+    std::lock_guard<std::mutex> call(m->call_mu);
+    const uint32_t n = (uint32_t)m->dv.size();
+    const uint32_t total = prm->samples == 0 ? 1 : prm->samples;
+    // phase 1: every device uploads the scene and launches its sample range (workers 1..n-1; this thread is device 0)
     {
-        std::vector<std::thread> th;
-        for (uint32_t k = 1; k < n_devices; ++k) th.emplace_back(work, k);
-        work(0);
-        for (auto& t : th) t.join();
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->desc = desc; m->cam = cam; m->prm = prm;
+        m->pending = n - 1; ++m->generation;
     }
+    if (n > 1) m->cv_go.notify_all();
+    int prev_dev = -1; cudaGetDevice(&prev_dev);
+    multi_device_job(m, 0);
+    if (n > 1) { std::unique_lock<std::mutex> lk(m->mu); m->cv_done.wait(lk, [&] { return m->pending == 0; }); }
     int rc = B200RT_OK;
-    for (auto& d : dv) if (d.rc && rc == B200RT_OK) { rc = d.rc; g_last_error = d.err; }
-    // phase 2 on the first device: wait for everyone, fused sum + resolve over peer access, copy the frame out
-    uint8_t* d_rgb = nullptr;
-    int dev0 = -1;
-    if (rc == B200RT_OK) rc = resolve_device(dv[0].id, &dev0);
+    for (auto& d : m->dv) if (d.rc && rc == B200RT_OK) { rc = d.rc; g_last_error = d.err; }
+    // phase 2 on the first device: stream-ordered wait for everyone, fused sum + resolve over peer access, frame copy-back
+    B200rtMulti::Dev& d0 = m->dv[0];
+    if (rc == B200RT_OK && cudaSetDevice(d0.id) != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaSetDevice(%d) failed", d0.id);
+    if (rc == B200RT_OK && m->rgb_bytes < px * 3) {
+        cudaFree(m->d_rgb); m->d_rgb = nullptr; m->rgb_bytes = 0;
+        if (cudaMalloc(&m->d_rgb, px * 3) != cudaSuccess) rc = fail(B200RT_ENOMEM, "rgb8 buffer"); else m->rgb_bytes = px * 3;
+    }
     if (rc == B200RT_OK) {
-        DeviceGuard guard(dev0);
-        for (uint32_t k = 1; k < n_devices && rc == B200RT_OK; ++k) {
-            int can = 0, devk = 0;
-            resolve_device(dv[k].id, &devk);
-            cudaDeviceCanAccessPeer(&can, dev0, devk);
-            if (!can) { rc = fail(B200RT_ECUDA, "device %d cannot access device %d's memory (no peer path)", dev0, devk); break; }
-            cudaError_t e = cudaDeviceEnablePeerAccess(devk, 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
-            if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", devk, cudaGetErrorString(e));
+        const float* ptrs[MAX_PEERS];
+        for (uint32_t k = 0; k < n; ++k) {
+            ptrs[k] = m->dv[k].accum;
+            if (k && cudaStreamWaitEvent(d0.stream, m->dv[k].done, 0) != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaStreamWaitEvent failed");
         }
-        if (rc == B200RT_OK && cudaMalloc(&d_rgb, px * 3) != cudaSuccess) rc = fail(B200RT_ENOMEM, "rgb8 buffer");
+        if (rc == B200RT_OK) rc = b200rt_resolve_peers_rgb8_device(ptrs, n, cam->image_width, cam->image_height, total, 0, 0, m->d_rgb, nullptr, d0.stream);
         if (rc == B200RT_OK) {
-            const float* ptrs[MAX_PEERS];
-            for (uint32_t k = 0; k < n_devices; ++k) {
-                ptrs[k] = dv[k].accum;
-                if (k && cudaStreamWaitEvent(dv[0].stream, dv[k].done, 0) != cudaSuccess) rc = fail(B200RT_ECUDA, "cudaStreamWaitEvent failed");
-            }
-            if (rc == B200RT_OK) rc = b200rt_resolve_peers_rgb8_device(ptrs, n_devices, cam->image_width, cam->image_height, total, 0, 0, d_rgb, dv[0].stream);
-            if (rc == B200RT_OK) {
-                cudaError_t e = cudaMemcpyAsync(out_rgb8, d_rgb, px * 3, cudaMemcpyDeviceToHost, dv[0].stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(dv[0].stream);
-                if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "frame copy-back: %s", cudaGetErrorString(e));
-            }
+            cudaError_t e = cudaMemcpyAsync(out_rgb8, m->d_rgb, px * 3, cudaMemcpyDeviceToHost, d0.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(d0.stream);
+            if (e != cudaSuccess) rc = fail(B200RT_ECUDA, "frame copy-back: %s", cudaGetErrorString(e));
         }
     }
-    // statistics + teardown (every device is idle once device 0's stream has drained; on an error path drain each)
+    // statistics + per-frame teardown: every device is idle once device 0's stream has drained (on an error path drain each)
     if (stats) memset(stats, 0, sizeof *stats);
-    for (auto& d : dv) {
-        int dev = 0;
-        if (resolve_device(d.id, &dev) != B200RT_OK) continue;
-        DeviceGuard guard(dev);
-        if (d.stream) cudaStreamSynchronize(d.stream);
+    std::string keep = g_last_error;
+    for (auto& d : m->dv) {
+        DeviceGuard guard(d.id);
+        if (rc != B200RT_OK && d.stream) cudaStreamSynchronize(d.stream);
         if (d.ran) {
             B200rtStats st{};
             if (b200rt_render_device_finish(d.scene, d.stream, &st) == B200RT_OK && stats) {
@@ -836,14 +896,33 @@ int b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, ui
                 stats->kernel_ms = std::max(stats->kernel_ms, st.kernel_ms); stats->total_ms = std::max(stats->total_ms, st.total_ms);
             }
         }
-        if (d.scene) b200rt_scene_destroy(d.scene);
-        if (d.accum) cudaFree(d.accum);
-        if (d.done) cudaEventDestroy(d.done);
-        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.scene) { b200rt_scene_destroy(d.scene); d.scene = nullptr; }
     }
-    if (d_rgb && dev0 >= 0) { DeviceGuard guard(dev0); cudaFree(d_rgb); }
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    if (rc != B200RT_OK) g_last_error = keep;
     if (stats && rc == B200RT_OK) stats->launches += 1;
     return rc;
+}
+
+// One-shot form: the handle for this device list is created on first use and kept for the life of the process
+// (a host that calls render_scene once per frame pays the stream / buffer / peer-access / thread set-up once).
+int b200rt_render_rgb8_multi(const B200rtSceneDesc* desc, const int* devices, uint32_t n_devices, const B200rtCamera* cam,
+                             const B200rtRenderParams* prm, uint8_t* out_rgb8, B200rtStats* stats) {
+    if (!desc || !devices || !cam || !prm || !out_rgb8) return fail(B200RT_EINVAL, "NULL argument");
+    if (n_devices < 1 || n_devices > (uint32_t)MAX_PEERS) return fail(B200RT_EINVAL, "n_devices %u outside [1, %d]", n_devices, MAX_PEERS);
+    B200rtMulti* m = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_multi_mu);
+        std::vector<int> key(devices, devices + n_devices);
+        auto it = g_multi_cache.find(key);
+        if (it != g_multi_cache.end()) m = it->second;
+        else {
+            int rc = b200rt_multi_create(devices, n_devices, &m);
+            if (rc) return rc;
+            g_multi_cache[key] = m;
+        }
+    }
+    return b200rt_multi_render_rgb8(m, desc, cam, prm, out_rgb8, stats);
 }
 
 int b200rt_resolve_rgb8_device(const float* d_accum, uint32_t W, uint32_t H, uint32_t samples, uint8_t* d_out, void* cuda_stream) {
@@ -915,14 +994,15 @@ int b200rt_peer_wait_device(uint32_t* d_my_flags, uint32_t n_peers, uint32_t slo
     CU(cudaGetLastError());
     return B200RT_OK;
 }
-int b200rt_peer_timed_out(const uint32_t* d_my_flags, uint32_t* out) {
+int b200rt_peer_timed_out(uint32_t* d_my_flags, uint32_t* out) {
     if (!d_my_flags || !out) return fail(B200RT_EINVAL, "NULL argument");
     CU(cudaMemcpy(out, d_my_flags + 2 * PEER_FLAG_STRIDE, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (*out) CU(cudaMemset(d_my_flags + 2 * PEER_FLAG_STRIDE, 0, sizeof(uint32_t)));   // reported once: a later frame starts clean
     return B200RT_OK;
 }
 
 int b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_peers, uint32_t W, uint32_t H, uint32_t samples,
-                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, void* cuda_stream) {
+                                     uint32_t row_begin, uint32_t row_end, uint8_t* d_out, const uint32_t* d_my_flags, void* cuda_stream) {
     if (!d_accums || !d_out || W == 0 || H == 0) return fail(B200RT_EINVAL, "bad argument");
     if (n_peers < 1 || n_peers > (uint32_t)MAX_PEERS) return fail(B200RT_EINVAL, "n_peers %u outside [1, %d]", n_peers, MAX_PEERS);
     if (row_begin == 0 && row_end == 0) row_end = H;
@@ -934,6 +1014,7 @@ int b200rt_resolve_peers_rgb8_device(const float* const* d_accums, uint32_t n_pe
         a.accum[r] = reinterpret_cast<const float4*>(d_accums[r]);
     }
     a.n_peers = n_peers; a.W = W; a.H = H; a.samples = samples; a.row_begin = row_begin; a.row_end = row_end; a.out = d_out;
+    a.abort_flag = d_my_flags ? d_my_flags + 2 * PEER_FLAG_STRIDE : nullptr;    // the word peer_wait_kernel sets on a time-out
     dim3 block(128, 1), grid(((W + 3) / 4 + 127) / 128, row_end - row_begin);
     resolve_peers_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>(a);
     CU(cudaGetLastError());
@@ -1009,7 +1090,6 @@ int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, 
     for (size_t i = 0; i < n; ++i) max_origin = std::max(max_origin, std::max(std::fabs(rays[i].ox), std::max(std::fabs(rays[i].oy), std::fabs(rays[i].oz))));
     const char* fs = getenv("B200RT_FAST_SLAB");
     bool fast = sc->box_pad >= 4.0f * 1.1920929e-7f * max_origin && !(fs && atoi(fs) == 0);
-    if (fast) a.scene.nodes = sc->ds.cnodes;
     if (plan.all_in_smem) rc = fast ? go(closest_hit_kernel<SmemAcc, true, true>) : go(closest_hit_kernel<SmemAcc, true, false>);
     else rc = fast ? go(closest_hit_kernel<GmemAcc, true, true>) : go(closest_hit_kernel<GmemAcc, true, false>);
     if (rc == B200RT_OK) {

@@ -28,6 +28,8 @@ struct BvhBuildResult {
     uint32_t depth = 0;             // max number of inner nodes on a root-to-leaf path
 };
 
+constexpr uint32_t BVH_MAX_DEPTH = 60;     // levels the device traversal stack holds (b200rt.cu checks the same bound)
+
 namespace detail {
 inline void box_init(HostBox& b) { for (int a = 0; a < 3; ++a) { b.lo[a] = INFINITY; b.hi[a] = -INFINITY; } }
 inline void box_grow(HostBox& b, const HostBox& o) { for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], o.lo[a]); b.hi[a] = std::max(b.hi[a], o.hi[a]); } }
@@ -86,7 +88,11 @@ struct Builder {
                              [axis](const BuildPrim& x, const BuildPrim& y) { return x.centroid[axis] < y.centroid[axis] || (x.centroid[axis] == y.centroid[axis] && x.code < y.code); });
             return mid;
         };
-        if (!(ext[wide] > 0.0f) || depth >= 56) return median_split(wide);   // coincident centroids / depth guard
+        // Depth guard: the device traversal stack holds 60 levels.  A median split halves the range, so a subtree of n
+        // primitives built by median splits alone is ceil(log2 n) deep: switch to them while that still fits (a SAH
+        // split of a strongly clustered scene can peel one primitive per level).
+        uint32_t log2n = 0; while ((size_t(1) << log2n) < n) ++log2n;
+        if (!(ext[wide] > 0.0f) || depth + log2n >= BVH_MAX_DEPTH - 2) return median_split(wide);   // coincident centroids / depth guard
 
         float best_cost = INFINITY; int best_axis = -1; size_t best_mid = 0;
         if (n <= 64) {

@@ -123,7 +123,7 @@ __device__ __forceinline__ void to_center(float lo, float hi, float* c, float* h
 }
 
 __global__ void emit_kernel(const PrimBox* __restrict__ prims, const uint32_t* __restrict__ order, int n, const int2* __restrict__ children,
-                            const SubBox* __restrict__ sub, BvhNode* nodes, BvhNode* cnodes) {
+                            const SubBox* __restrict__ sub, BvhNode* nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int2 c = children[i];
@@ -133,20 +133,18 @@ __global__ void emit_kernel(const PrimBox* __restrict__ prims, const uint32_t* _
     int r0 = c.x >= 0 ? c.x : ~__float_as_int(prims[order[~c.x]].lo.w);   // leaf: ~((type << 28) | id)
     int r1 = c.y >= 0 ? c.y : ~__float_as_int(prims[order[~c.y]].lo.w);
     BvhNode q;
-    q.q0 = make_float4(l0[0], l0[1], l0[2], h0[0]); q.q1 = make_float4(h0[1], h0[2], l1[0], l1[1]);
-    q.q2 = make_float4(l1[2], h1[0], h1[1], h1[2]); q.q3 = make_float4(__int_as_float(r0), __int_as_float(r1), 0.f, 0.f);
-    nodes[i] = q;
+    q.q3 = make_float4(__int_as_float(r0), __int_as_float(r1), 0.f, 0.f);
     float cc0[3], hh0[3], cc1[3], hh1[3];
     for (int k = 0; k < 3; ++k) { to_center(l0[k], h0[k], &cc0[k], &hh0[k]); to_center(l1[k], h1[k], &cc1[k], &hh1[k]); }
     q.q0 = make_float4(cc0[0], cc0[1], cc0[2], hh0[0]); q.q1 = make_float4(hh0[1], hh0[2], cc1[0], cc1[1]);
     q.q2 = make_float4(cc1[2], hh1[0], hh1[1], hh1[2]);
-    cnodes[i] = q;
+    nodes[i] = q;
 }
 
 // Builds the tree of `prims` (host array, boxes already padded; at least 2 entries) into
-// d_nodes / d_cnodes (n - 1 nodes each, root = 0).  Returns a cudaError_t; *depth_out = the
+// d_nodes (n - 1 nodes in the centre/half-extent form, root = 0).  Returns a cudaError_t; *depth_out = the
 // largest number of inner nodes on a root-to-leaf path.
-inline cudaError_t build(const std::vector<BuildPrim>& prims, const HostBox& bounds, BvhNode* d_nodes, BvhNode* d_cnodes, uint32_t* depth_out, float* build_ms) {
+inline cudaError_t build(const std::vector<BuildPrim>& prims, const HostBox& bounds, BvhNode* d_nodes, uint32_t* depth_out, float* build_ms) {
     const int n = (int)prims.size();
     std::vector<PrimBox> hp(n);
     for (int i = 0; i < n; ++i) {
@@ -192,7 +190,7 @@ inline cudaError_t build(const std::vector<BuildPrim>& prims, const HostBox& bou
     LBVH_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 63));
     hierarchy_kernel<<<(n - 1 + T - 1) / T, T>>>(d_keys2, n, d_children, d_pi, d_pl);
     refit_kernel<<<(n + T - 1) / T, T>>>(d_prims, d_vals2, n, d_children, d_pi, d_pl, d_sub, d_arr);
-    emit_kernel<<<(n - 1 + T - 1) / T, T>>>(d_prims, d_vals2, n, d_children, d_sub, d_nodes, d_cnodes);
+    emit_kernel<<<(n - 1 + T - 1) / T, T>>>(d_prims, d_vals2, n, d_children, d_sub, d_nodes);
     LBVH_TRY(cudaGetLastError());
     LBVH_TRY(cudaEventRecord(e1));
     SubBox root;

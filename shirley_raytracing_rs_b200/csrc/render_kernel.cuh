@@ -8,7 +8,7 @@ namespace b200rt {
 // ------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------
-constexpr int BLOCK = 256;          // threads per CTA (8 warps)
+constexpr int BLOCK = 256;          // threads per CTA of the parity-hook kernels (K1); the render kernel's CTA size is its BLK template argument (768 by default)
 constexpr size_t LBVH_AUTO_MIN = 262144;   // primitives from which scene_create builds the tree on the device
 constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
 
@@ -35,18 +35,10 @@ struct RenderArgs {
     uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
     uint32_t shard_count, shard_index;
     uint32_t accumulate;
-    uint32_t trav_threshold;                    // v2: leave the traversal loop when fewer lanes than this still traverse
-    uint32_t wf_inner, wf_fetch, wf_park;       // v3 thresholds (see path_trace_kernel_v3)
+    uint32_t trav_threshold;                    // leave the traversal loop when fewer lanes than this still traverse
     float4* accum;
     Counters* counters;
 };
-
-__device__ __forceinline__ TopPrims top_of(const DeviceScene& s) {
-    TopPrims t; t.n = s.n_top_prims;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) t.code[k] = s.top_prims[k];
-    return t;
-}
 
 // Stage the scene (or the top of the BVH) into shared memory and set up the accessor.
 // Shared layout: [nodes][geom][mats][tex][stack: stack_depth x BLOCK ints]
@@ -86,11 +78,14 @@ constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + 
 
 // Per-pixel sums as 64-bit fixed point (2^-32) in shared memory: integer adds commute, so the
 // result does not depend on which lane traced which sample, nor on scheduling or sharding.
-__device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v) {
-    // 2^-32 fixed point; non-finite contributions are dropped (a NaN sample would blacken the
-    // reference's pixel; here it contributes nothing)
+// Contract: a sample whose radiance is NaN or infinite contributes nothing (the reference would
+// carry the NaN into the pixel, which to_image writes as 0).  Each channel of a finite sample is clamped to +-`lim` =
+// 2e9 / samples-per-call, so a pixel's 2^-32 fixed-point sum (63 bits: |sum| < 2^31 = 2.1e9) cannot wrap whatever the
+// emitters' strength; a clamped sample still saturates the pixel (to_image clips the mean at 1).
+__device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v, float lim) {
     const float S = 4294967296.0f;
     if (fabsf(v.x + v.y + v.z) <= 3.0e38f) {   // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative)
+        v.x = fminf(fmaxf(v.x, -lim), lim); v.y = fminf(fmaxf(v.y, -lim), lim); v.z = fminf(fmaxf(v.z, -lim), lim);
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
@@ -133,6 +128,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                      + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
     const float T_MIN = 0.001f;                      // render.rs:31
     const bool has_perlin = a.scene.perlin != nullptr;
+    const float sample_lim = 2.0e9f / (float)a.samples;   // acc_add: the per-call fixed-point sum cannot wrap
 
     unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
     // lane-utilisation diagnostics (COUNT only, lane 0 of each warp):
@@ -209,7 +205,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                     else { ray.o = so.o; ray.d = so.d; setup = true; }
                 }
             }
-            if (done) { acc_add(wacc, pl, emit); alive = false; }
+            if (done) { acc_add(wacc, pl, emit, sample_lim); alive = false; }
 
             // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
             // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG

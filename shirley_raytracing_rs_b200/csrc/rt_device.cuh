@@ -12,12 +12,14 @@ namespace b200rt {
 // ------------------------------------------------------------------------------------------
 // Device scene layout (all arrays 16-byte aligned, read-only during a launch)
 // ------------------------------------------------------------------------------------------
-// BVH2 inner node, 64 B = 4 x float4 (one 16-byte vector load each):
-//   q0 = (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x)
-//   q1 = (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y)
-//   q2 = (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z)
+// BVH2 inner node, 64 B = 4 x float4 (one 16-byte vector load each); each child box is stored as
+// centre c and half-extent h (the three-FMA slab test below), rounded outwards from (lo, hi):
+//   q0 = (c0.c.x, c0.c.y, c0.c.z, c0.h.x)
+//   q1 = (c0.h.y, c0.h.z, c1.c.x, c1.c.y)
+//   q2 = (c1.c.z, c1.h.x, c1.h.y, c1.h.z)
 //   q3 = (bits(child0), bits(child1), 0, 0)
 // child >= 0: inner-node index; child < 0: leaf, ~child = (prim_type << 28) | hit_id.
+// An empty child has h = -1 (never entered), an unbounded one c = 0, h = 3e38.
 // The boxes of BOTH children live in the parent, so one node fetch feeds two slab tests
 // (the reference's TreeNode is 72 B of f64 per box and tests at pop, bvh/bbox_tree.rs:16-20,
 // :73-76).  Nodes are stored breadth-first: the first K nodes are the top of the tree and
@@ -46,8 +48,7 @@ struct ImageRec { const uchar4* texels; uint32_t width, height; uint32_t pad; };
 struct PerlinRec { float4 ranfloat[256]; uint8_t perm_x[256], perm_y[256], perm_z[256]; };
 
 struct DeviceScene {
-    const BvhNode* nodes;
-    const BvhNode* cnodes;      // same tree, child boxes as (centre.xyz, half.xyz): the render kernel's slab test
+    const BvhNode* nodes;       // ONE copy of the tree, child boxes as (centre.xyz, half.xyz)
     const GeomRec* geom;
     const MatRec* mats;
     const TexRec* tex;
@@ -174,9 +175,9 @@ __device__ __forceinline__ float rcp_exact(float x) { return __frcp_rn(x); }
 
 struct RayF {
     float3 o, d;
-    float3 inv;         // 1/d for the BOX tests only: IEEE from make_ray, 1-ulp approximate from
-                        // make_ray_fast (boxes only cull and are padded).  Primitive tests take
-                        // their own IEEE reciprocals so they stay bit-reproducible on the CPU.
+    float3 inv;         // 1/d for the BOX tests only (clamped to +-1e18 for the centre-form slab test: boxes
+                        // only cull and are padded).  Primitive tests take their own IEEE reciprocals so
+                        // they stay bit-reproducible on the CPU.
     float3 ood;         // o * inv, for the one-FMA-per-plane slab test
     float a;            // d.d
 };
@@ -188,21 +189,11 @@ __device__ __forceinline__ RayF make_ray(float3 o, float3 d) {
     r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
     return r;
 }
-// Traversal-only ray: MUFU.RCP reciprocals (max error 1 ulp) feed aabb_fast, whose boxes are
-// padded by ~34 ulp of the scene extent.  The reciprocal is clamped to +-1e18: with an
-// infinite one (direction component exactly 0) the one-FMA plane distance of an origin inside
-// the slab is inf - inf = NaN on one plane and -inf on the other, which would cull a box the
-// ray is inside of; a huge finite value keeps the far plane at +huge and the error analysis
+// The slab tests take a reciprocal clamped to +-1e18: with an infinite one (direction component exactly 0) the
+// one-FMA plane distance of an origin inside the slab is inf - inf = NaN on one plane and -inf on the other, which
+// would cull a box the ray is inside of; a huge finite value keeps the far plane at +huge and the error analysis
 // (everything scales with |inv|) unchanged.
 __device__ __forceinline__ float clamp_inv(float x) { return fminf(fmaxf(x, -1e18f), 1e18f); }
-__device__ __forceinline__ RayF make_ray_fast(float3 o, float3 d) {
-    RayF r;
-    r.o = o; r.d = d;
-    r.inv = f3(clamp_inv(__fdividef(1.0f, d.x)), clamp_inv(__fdividef(1.0f, d.y)), clamp_inv(__fdividef(1.0f, d.z)));
-    r.ood = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
-    r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
-    return r;
-}
 // Shading-only ray (no reciprocals).
 __device__ __forceinline__ RayF make_ray_shade(float3 o, float3 d) {
     RayF r;
@@ -234,28 +225,13 @@ __device__ __forceinline__ bool aabb_hit2(const RayF& r, float lox, float loy, f
     return !(hi <= lo);
 }
 
-// One-FMA-per-plane slab test used by the render kernels: t = plane * inv - o * inv.
-// Against (plane - o) * inv it carries an extra absolute error of eps * |o * inv| per axis,
-// i.e. eps * |o| in space; the BVH boxes are padded by more than that (scene_create), so a
-// box can only be entered EARLY: the test is conservative and the closest hit unchanged.
-// min/max form (no sign selects); fminf/fmaxf drop NaN planes (0 * inf) like aabb_hit2.
-__device__ __forceinline__ bool aabb_fast(const RayF& r, float lox, float loy, float loz, float hix, float hiy, float hiz,
-                                          float t_min, float t_max, float* t_enter) {
-    float ax = fmaf(lox, r.inv.x, -r.ood.x), bx = fmaf(hix, r.inv.x, -r.ood.x);
-    float ay = fmaf(loy, r.inv.y, -r.ood.y), by = fmaf(hiy, r.inv.y, -r.ood.y);
-    float az = fmaf(loz, r.inv.z, -r.ood.z), bz = fmaf(hiz, r.inv.z, -r.ood.z);
-    float lo = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
-    float hi = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_max));
-    *t_enter = lo;
-    return lo <= hi;
-}
-
-// Slab test on a box given as centre + half-extent (DeviceScene::cnodes): per axis
+// Slab test on a box given as centre + half-extent: per axis
 //   t_c = c * inv - o * inv,   t_near = t_c - h |inv|,   t_far = t_c + h |inv|
-// — three FMAs and no min/max pair.  ncu on the min/max form: the ALU pipe (FMNMX, selects,
+// — three FMAs and no min/max pair.  Against (plane - o) * inv each plane carries an extra absolute error of
+// eps * |o * inv| (eps * |o| in space) plus eps * |c| for the centre; the BVH boxes are padded by more than that
+// (scene_create), so a box can only be entered EARLY: the test is conservative and the closest hit unchanged.  ncu on the min/max form: the ALU pipe (FMNMX, selects,
 // integer ops; half the FMA pipes' rate on sm_100) was 58 % busy against 23 % for the FMA pipes,
-// with 10 ALU-pipe operations per box; this form has 4.  Error analysis as for aabb_fast plus
-// eps * |c| for the centre: covered by the same box padding (scene_create).
+// with 10 ALU-pipe operations per box; this form has 4.  
 __device__ __forceinline__ void aabb_center(const RayF& r, float cx, float cy, float cz, float hx, float hy, float hz,
                                             float t_min, float t_max, float* lo, float* hi) {
     float tx = fmaf(cx, r.inv.x, -r.ood.x), ty = fmaf(cy, r.inv.y, -r.ood.y), tz = fmaf(cz, r.inv.z, -r.ood.z);
@@ -400,53 +376,6 @@ __device__ __forceinline__ void hit_leaf(const RayF& r, const Acc& acc, int leaf
 // ------------------------------------------------------------------------------------------
 struct TravCounters { uint32_t nodes, prims; };
 
-struct TopPrims { uint32_t n; int code[7]; };
-
-// The up-front list (DeviceScene::top_prims): same code for every lane, no divergence.
-template <bool COUNT, class Acc>
-__device__ __forceinline__ void hit_top_prims(const RayF& r, const Acc& acc, const TopPrims& top, float t_min, Closest& c, TravCounters& tc,
-                                              const float3* inv_e = nullptr) {
-#pragma unroll 1
-    for (uint32_t k = 0; k < top.n; ++k) {
-        if (COUNT) tc.prims++;
-        hit_leaf(r, acc, top.code[k], t_min, c, inv_e);
-    }
-}
-
-template <bool COUNT, class Acc>
-__device__ __forceinline__ void closest_hit(const RayF& r, const Acc& acc, const TopPrims& top, int* stack, int stride,
-                                            float t_min, Closest& c, TravCounters& tc) {
-    int sp = 0;
-    int node = 0;
-    hit_top_prims<COUNT>(r, acc, top, t_min, c, tc);
-    for (;;) {
-        if (node >= 0) {
-            float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
-            if (COUNT) tc.nodes++;
-            float e0, e1;
-            bool h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
-            bool h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
-            int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            if (h0 && h1) {
-                bool swap = e1 < e0;
-                int near_c = swap ? c1 : c0, far_c = swap ? c0 : c1;
-                stack[sp * stride] = far_c; ++sp;
-                node = near_c;
-            } else if (h0) node = c0;
-            else if (h1) node = c1;
-            else {
-                if (sp == 0) break;
-                --sp; node = stack[sp * stride];
-            }
-        } else {
-            if (COUNT) tc.prims++;
-            hit_leaf(r, acc, node, t_min, c);
-            if (sp == 0) break;
-            --sp; node = stack[sp * stride];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // Resumable traversal for the persistent render kernel.  The cursor (node, sp) lives in
 // registers between calls so a lane can be parked while other lanes of its warp shade.
@@ -454,37 +383,8 @@ __device__ __forceinline__ void closest_hit(const RayF& r, const Acc& acc, const
 // ------------------------------------------------------------------------------------------
 #define B200RT_TRAV_DONE 0x7fffffff
 
-// One inner-node visit: fetch the node, test both children, descend into the nearer hit
-// child, push the farther one; with no hit, pop (or finish).
-template <bool COUNT, bool FAST, class Acc>
-__device__ __forceinline__ void trav_inner(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, const Closest& c,
-                                           int& node, int& sp, TravCounters& tc) {
-    float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
-    if (COUNT) tc.nodes++;
-    float e0, e1;
-    bool h0, h1;
-    if (FAST) {
-        h0 = aabb_fast(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
-        h1 = aabb_fast(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
-    } else {
-        h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &e0);
-        h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &e1);
-    }
-    int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-    if (h0 && h1) {
-        bool swap = e1 < e0;
-        stack[sp * stride] = swap ? c0 : c1; ++sp;
-        node = swap ? c1 : c0;
-    } else if (h0 || h1) {
-        node = h0 ? c0 : c1;
-    } else if (sp > 0) {
-        --sp; node = stack[sp * stride];
-    } else {
-        node = B200RT_TRAV_DONE;
-    }
-}
-
-// Variants for the v2 render kernel.  The stack is addressed through a moving pointer
+// One inner-node visit: fetch the node, test both children, descend into the nearer hit child, push the farther one;
+// with no hit, pop (or finish).  The stack is addressed through a moving pointer
 // (`top` = next free slot of this lane's column) and its element 0 holds B200RT_TRAV_DONE, so a
 // pop needs neither an index multiply nor an emptiness test: the sentinel ends the traversal.
 // The step is written branch-free (selects + one predicated store / load): the three outcomes
@@ -495,13 +395,15 @@ __device__ __forceinline__ void trav_inner_s(const RayF& r, const Acc& acc, uint
     float4 q0 = acc.node_q(node, 0), q1 = acc.node_q(node, 1), q2 = acc.node_q(node, 2), q3 = acc.node_q(node, 3);
     if (COUNT) tc.nodes++;
     float lo0, hi0, lo1, hi1;
-    if (FAST) {   // `nodes` is the centre/half-extent copy (DeviceScene::cnodes)
+    if (FAST) {
         aabb_center(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &lo0, &hi0);
         aabb_center(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &lo1, &hi1);
     } else {
-        // aabb_hit2's verdict as an interval: a miss becomes an empty one
-        bool h0 = aabb_hit2(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min, c.t, &lo0);
-        bool h1 = aabb_hit2(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min, c.t, &lo1);
+        // Exact path (ray origins far outside the scene, B200RT_FAST_SLAB=0): Aabb::hit2's arithmetic on the box
+        // [c - h, c + h] (a superset of the primitive's box: a box only culls).  Its verdict as an interval: a miss
+        // becomes an empty one.
+        bool h0 = aabb_hit2(r, q0.x - q0.w, q0.y - q1.x, q0.z - q1.y, q0.x + q0.w, q0.y + q1.x, q0.z + q1.y, t_min, c.t, &lo0);
+        bool h1 = aabb_hit2(r, q1.z - q2.y, q1.w - q2.z, q2.x - q2.w, q1.z + q2.y, q1.w + q2.z, q2.x + q2.w, t_min, c.t, &lo1);
         hi0 = h0 ? INFINITY : -INFINITY; hi1 = h1 ? INFINITY : -INFINITY;
         lo0 = h0 ? lo0 : 0.0f; lo1 = h1 ? lo1 : 0.0f;
     }
@@ -542,14 +444,6 @@ __device__ __forceinline__ void trav_leaf_s(const RayF& r, const Acc& acc, uint3
     hit_leaf(r, acc, node, t_min, c);
     top -= stride_bytes;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(node) : "r"(top) : "memory");
-}
-
-template <bool COUNT, class Acc>
-__device__ __forceinline__ void trav_leaf(const RayF& r, const Acc& acc, int* stack, int stride, float t_min, Closest& c,
-                                          int& node, int& sp, TravCounters& tc) {
-    if (COUNT) tc.prims++;
-    hit_leaf(r, acc, node, t_min, c);
-    if (sp > 0) { --sp; node = stack[sp * stride]; } else node = B200RT_TRAV_DONE;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -647,17 +541,6 @@ __device__ __forceinline__ float perlin_noise(const PerlinRec* __restrict__ P, f
                 accum += blend * (g.x * wx + g.y * wy + g.z * wz);
             }
     return accum;
-}
-
-__device__ __forceinline__ float perlin_turbulence(const PerlinRec* __restrict__ P, float3 p) {   // perlin/mod.rs:111-123, depth 7
-    float accum = 0.0f, weight = 1.0f;
-#pragma unroll 1
-    for (int d = 0; d < 7; ++d) {
-        accum += weight * perlin_noise(P, p);
-        weight *= 0.5f;
-        p = p * 2.0f;
-    }
-    return fabsf(accum);
 }
 
 // One out-of-line copy of the accurate sine (its large-argument path is ~150 instructions and
@@ -763,14 +646,6 @@ __device__ __forceinline__ float3 marble(float scale, float3 p, float turbulence
     return f3(noise, noise, noise);
 }
 
-template <class Acc>
-__device__ __forceinline__ float3 texture_value(const Acc& acc, const ImageRec* __restrict__ images, const PerlinRec* __restrict__ perlin,
-                                                int t, const HitRec& h) {
-    TexResult r = texture_descend(acc, images, t, h);
-    if (r.need_perlin) return marble(r.perlin_scale, h.p, perlin_turbulence(&perlin[r.perlin_idx], h.p));
-    return r.rgb;
-}
-
 // ------------------------------------------------------------------------------------------
 // Samplers (core/math.rs:33-81) — rejection loops in the reference's draw order
 // ------------------------------------------------------------------------------------------
@@ -863,14 +738,6 @@ __device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h,
     out.d = dir;
     atten = atten * a;
     return out;
-}
-
-template <class Acc>
-__device__ __forceinline__ ShadeOut shade(const DeviceScene& s, const Acc& acc, const RayF& r, const HitRec& h,
-                                          Rng& rng, float3& atten, float3& emit) {
-    ShadePrep p = shade_prepare(s, acc, h);
-    float3 a = p.tex.need_perlin ? marble(p.tex.perlin_scale, h.p, perlin_turbulence(&s.perlin[p.tex.perlin_idx], h.p)) : p.tex.rgb;
-    return shade_finish(r, h, p.m, a, rng, atten, emit);
 }
 
 // Camera::pixel_ray (camera/mod.rs:98-131); x, y are the jittered pixel coordinates.

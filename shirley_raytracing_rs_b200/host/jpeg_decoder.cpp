@@ -47,7 +47,7 @@ struct HuffTable {
         for (int l = 1; l <= 9; ++l) {
             for (int i = 0; i < bits[l]; ++i, ++k, ++code) {
                 int first = code << (9 - l);
-                for (int f = 0; f < (1 << (9 - l)); ++f) look[first + f] = (uint16_t)((l << 8) | vals[k]);
+                for (int f = 0; f < (1 << (9 - l)) && first + f < 512; ++f) look[first + f] = (uint16_t)((l << 8) | vals[k]);
             }
             code <<= 1;
         }
@@ -107,38 +107,39 @@ const uint8_t ZIGZAG[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4,
                             35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 inline uint8_t clamp8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+inline uint8_t clamp8_64(int64_t x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 
 // The accurate integer inverse DCT of libjpeg (jidctint.c, "islow"): Loeffler-Ligtenberg-
 // Moschytz factorisation, 13-bit fixed-point constants, two intermediate fraction bits.
 void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int stride) {
     const int CONST_BITS = 13, PASS1_BITS = 2;
-    const int32_t F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
+    const int64_t F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
                   F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
-    auto descale = [](int32_t x, int n) { return (x + (1 << (n - 1))) >> n; };
-    int32_t ws[64];
+    auto descale = [](int64_t x, int n) { return (x + (int64_t(1) << (n - 1))) >> n; };   // 64-bit: a corrupt stream's coefficients must not overflow (valid streams never reach 2^31)
+    int64_t ws[64];
     for (int pass = 0; pass < 2; ++pass) {
         for (int i = 0; i < 8; ++i) {
-            int32_t in[8];
-            if (pass == 0) for (int k = 0; k < 8; ++k) in[k] = (int32_t)coef[k * 8 + i] * (int32_t)q[k * 8 + i];
+            int64_t in[8];
+            if (pass == 0) for (int k = 0; k < 8; ++k) in[k] = (int64_t)coef[k * 8 + i] * (int64_t)q[k * 8 + i];
             else for (int k = 0; k < 8; ++k) in[k] = ws[i * 8 + k];
-            int32_t z2 = in[2], z3 = in[6];
-            int32_t z1 = (z2 + z3) * F_0_541;
-            int32_t tmp2 = z1 + z3 * (-F_1_847);
-            int32_t tmp3 = z1 + z2 * F_0_765;
-            int32_t tmp0 = (in[0] + in[4]) * (1 << CONST_BITS);
-            int32_t tmp1 = (in[0] - in[4]) * (1 << CONST_BITS);
-            int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+            int64_t z2 = in[2], z3 = in[6];
+            int64_t z1 = (z2 + z3) * F_0_541;
+            int64_t tmp2 = z1 + z3 * (-F_1_847);
+            int64_t tmp3 = z1 + z2 * F_0_765;
+            int64_t tmp0 = (in[0] + in[4]) * (1 << CONST_BITS);
+            int64_t tmp1 = (in[0] - in[4]) * (1 << CONST_BITS);
+            int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
             tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
             z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-            int32_t z4 = tmp1 + tmp3;
-            int32_t z5 = (z3 + z4) * F_1_175;
+            int64_t z4 = tmp1 + tmp3;
+            int64_t z5 = (z3 + z4) * F_1_175;
             tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
             z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
             z3 += z5; z4 += z5;
             tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
-            int32_t o[8] = {tmp10 + tmp3, tmp11 + tmp2, tmp12 + tmp1, tmp13 + tmp0, tmp13 - tmp0, tmp12 - tmp1, tmp11 - tmp2, tmp10 - tmp3};
+            int64_t o[8] = {tmp10 + tmp3, tmp11 + tmp2, tmp12 + tmp1, tmp13 + tmp0, tmp13 - tmp0, tmp12 - tmp1, tmp11 - tmp2, tmp10 - tmp3};
             if (pass == 0) for (int k = 0; k < 8; ++k) ws[k * 8 + i] = descale(o[k], CONST_BITS - PASS1_BITS);
-            else for (int k = 0; k < 8; ++k) out[i * stride + k] = clamp8(descale(o[k], CONST_BITS + PASS1_BITS + 3) + 128);
+            else for (int k = 0; k < 8; ++k) out[i * stride + k] = clamp8_64(descale(o[k], CONST_BITS + PASS1_BITS + 3) + 128);
         }
     }
 }
@@ -296,6 +297,15 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
                     for (int l = 1; l <= 16; ++l) { t.bits[l] = seg[i + l - 1]; total += t.bits[l]; }
                     i += 16;
                     if (total > 256 || i + total > n) throw Error("jpeg: bad DHT counts");
+                    {   // the code lengths must form a prefix code (Kraft): at most 2^l codes of length l remain at each
+                        // length, else build()'s canonical codes run past their tables (libjpeg: "bogus Huffman table")
+                        int code = 0;
+                        for (int l = 1; l <= 16; ++l) {
+                            code += t.bits[l];
+                            if (code > (1 << l)) throw Error("jpeg: over-subscribed Huffman table");
+                            code <<= 1;
+                        }
+                    }
                     memcpy(t.vals, seg + i, total); i += total;
                     t.build();
                 }
@@ -335,6 +345,7 @@ ImageData decode_jpeg(const uint8_t* data, size_t size) {
             case 0xEE: if (n >= 12 && memcmp(seg, "Adobe", 5) == 0) { adobe = true; adobe_transform = seg[11]; } break;
             case 0xDA: {   // SOS + entropy-coded data
                 if (!have_frame) throw Error("jpeg: scan before frame header");
+                if (n < 1) throw Error("jpeg: truncated SOS");
                 int ns = seg[0];
                 if (ns < 1 || ns > (int)comps.size() || n < (size_t)(1 + 2 * ns + 3)) throw Error("jpeg: bad SOS");
                 Scan sc; sc.progressive = progressive;

@@ -6,6 +6,8 @@
 
 #include <cstdlib>
 
+#include <dlfcn.h>
+
 #include "raytracer.hpp"
 
 namespace raytracer {
@@ -43,6 +45,18 @@ bool lookup_image(const std::string& name, ImageData* out) {
 // A deterministic procedural stand-in with the shape of assets/earthmap.jpg (1024x512 RGB8):
 // fBm "continents" over an ocean, ice caps at the poles.  Used when the embedding host has
 // not registered the real decoded JPEG (the asset is not part of this repository).
+// <directory of libb200rt.so>/assets/<file>: where the data the reference embeds in its binary ships here
+static std::string builtin_asset_path(const char* file) {
+    Dl_info info;
+    std::string dir = ".";
+    if (dladdr(reinterpret_cast<const void*>(&builtin_asset_path), &info) && info.dli_fname) {
+        std::string so = info.dli_fname;
+        size_t slash = so.find_last_of('/');
+        dir = slash == std::string::npos ? "." : so.substr(0, slash);
+    }
+    return dir + "/assets/" + file;
+}
+
 ImageData synthetic_earth(uint32_t W, uint32_t H) {
     ImageData im; im.width = W; im.height = H; im.rgb.resize((size_t)W * H * 3);
     auto hash = [](int x, int y, int z) { uint32_t h = (uint32_t)x * 374761393u + (uint32_t)y * 668265263u + (uint32_t)z * 2147483647u; h = (h ^ (h >> 13)) * 1274126177u; return (double)((h ^ (h >> 16)) & 0xFFFFFF) / 16777216.0; };
@@ -125,11 +139,14 @@ struct TextureManager {   // loader.rs:108-131
                 ImageData img;
                 if (!lookup_image(name, &img)) {
                     if (t.kind == TextureLoader::EarthBuiltin) {
-                        // the reference embeds assets/earthmap.jpg (image_texture.rs:11); that file is not part of
-                        // this repository: decode it when the host points at a copy, else the procedural stand-in
+                        // the reference embeds assets/earthmap.jpg in its binary (image_texture.rs:11,18-20); here the
+                        // same file ships next to the library (assets/earthmap.jpg) and is decoded on first use.
+                        // B200RT_EARTHMAP overrides the path; B200RT_EARTHMAP=synthetic selects a procedural stand-in.
                         const char* env = getenv("B200RT_EARTHMAP");
-                        if (env && *env) img = load_image_file(env);
-                        else img = synthetic_earth();
+                        if (env && !strcmp(env, "synthetic")) img = synthetic_earth();
+                        else if (env && *env) img = load_image_file(env);
+                        else img = load_image_file(builtin_asset_path("earthmap.jpg"));
+                        register_image(name, img);      // decode once per process
                     } else {
                         img = load_image_file(t.path);   // image_texture.rs:23-26 `image::open(path)?` (JPEG and PNG here)
                     }

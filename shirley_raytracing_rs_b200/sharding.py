@@ -34,7 +34,7 @@ def sample_ranges(total_samples: int, world: int) -> list[SampleRange]:
 
 
 def weak_sample_range(samples_per_rank: int, rank: int) -> SampleRange:
-    """Weak scaling (bench.py): every rank adds `samples_per_rank` new samples."""
+    """Weak scaling (bench.py --scaling weak): every rank adds `samples_per_rank` new samples."""
     return SampleRange(rank * samples_per_rank, samples_per_rank)
 
 
@@ -144,9 +144,11 @@ class PeerFrame:
         if self.barrier == "flags" and self.epoch > 0:
             self._wait(1, stream_ptr)
 
-    def combine(self, total_samples: int, stream_ptr=None):
+    def combine(self, total_samples: int, stream_ptr=None, events=None):
         """Collective.  Orders this rank's render before the peers' reads, resolves this rank's band of rows from
-        all ranks' buffers into the root's frame, and publishes 'done reading'."""
+        all ranks' buffers into the root's frame, and publishes 'done reading'.  `events(k)`, if given, is called
+        after stage k (0: the ranks are ordered, 1: the band is resolved, 2: 'done' is published) — bench.py's
+        per-frame cost breakdown records a CUDA event there."""
         F = self._F
         self.epoch += 1
         if self.barrier == "flags":
@@ -154,28 +156,54 @@ class PeerFrame:
             self._wait(0, stream_ptr)
         else:
             self.sync()
+        if events:
+            events(0)
+        # the flag array rides along: after a wait that timed out the kernel stores nothing (no frame from incomplete buffers)
         F.check(F.lib.b200rt_resolve_peers_rgb8_device(self._ptr_array, self.world, self.W, self.H, total_samples,
-                                                      self.band[0], self.band[1], self.frame_ptr, stream_ptr))
+                                                      self.band[0], self.band[1], self.frame_ptr,
+                                                      self.flag_ptr if self.barrier == "flags" else None, stream_ptr))
+        if events:
+            events(1)
         if self.barrier == "flags":
             self._signal(1, stream_ptr)
         else:
             self.sync()
+        if events:
+            events(2)
 
     def accum(self):
         """This rank's accumulation buffer as an (H, W, 4) float32 torch tensor (no copy)."""
         return self._torch.as_tensor(_DevicePtr(self.accum_ptr.value, (self.H, self.W, 4), "<f4"), device=self._torch.device("cuda", self.device))
 
-    def frame(self, stream_ptr=None):
-        """The assembled RGB8 frame, (H, W, 3) uint8, top row first; ordered after every rank's band (call after combine)."""
+    def wait_frame(self, stream_ptr=None):
+        """Stream-ordered: work enqueued after this starts after EVERY rank's band has landed in the root's frame."""
         if self.barrier == "flags" and self.epoch > 0:
             self._wait(1, stream_ptr)
+
+    def frame_tensor(self):
+        """The frame buffer as an (H, W, 3) uint8 torch tensor, no ordering and no check (pair with wait_frame + check)."""
+        return self._torch.as_tensor(_DevicePtr(self.frame_ptr.value, (self.H, self.W, 3), "|u1"), device=self._torch.device("cuda", self.device))
+
+    def frame(self, stream_ptr=None):
+        """The assembled RGB8 frame, (H, W, 3) uint8, top row first; ordered after every rank's band (call after combine).
+        Raises if a flag wait of this or an earlier frame gave up on a peer (the frame would be incomplete)."""
+        self.wait_frame(stream_ptr)
+        self.check()
         return self._torch.as_tensor(_DevicePtr(self.frame_ptr.value, (self.H, self.W, 3), "|u1"), device=self._torch.device("cuda", self.device))
 
     def timed_out(self) -> int:
-        """0, or 1 + the rank a flag wait gave up on (a peer died or never called combine)."""
+        """0, or 1 + the rank a flag wait gave up on (a peer died or never called combine).  Synchronises the device;
+        a reported time-out is cleared, so the next frame starts clean."""
         out = self._C.c_uint32()
         self._F.check(self._F.lib.b200rt_peer_timed_out(self.flag_ptr, self._C.byref(out)))
         return out.value
+
+    def check(self) -> None:
+        """Raise if a flag wait timed out since the last check: frames combined in between are not valid."""
+        t = self.timed_out() if self.barrier == "flags" else 0
+        if t:
+            raise RuntimeError(f"rank {self.rank}: peer flag wait timed out after {self.timeout_ms} ms (rank {t - 1} never arrived); "
+                               "the frame was not assembled")
 
     def close(self):
         F = self._F

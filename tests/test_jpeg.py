@@ -86,6 +86,43 @@ def test_rejects_bad_input(rt):
         rt.decode_jpeg(good[: len(good) // 3])          # truncated before the scan
 
 
+def _with_dht(bits, vals=b""):
+    """A minimal stream: SOI, one DHT segment with the given 16 code-length counts, EOI."""
+    seg = bytes([0x00]) + bytes(bits) + bytes(vals)
+    return b"\xff\xd8" + b"\xff\xc4" + (len(seg) + 2).to_bytes(2, "big") + seg + b"\xff\xd9"
+
+
+def test_rejects_oversubscribed_huffman_table(rt):
+    """A DHT whose code lengths are not a prefix code (255 codes of length 1) used to index the canonical-code
+    look-up table out of bounds; libjpeg calls this a bogus Huffman table."""
+    bits = [255] + [0] * 15
+    with pytest.raises(rt.B200rtError, match="over-subscribed"):
+        rt.decode_jpeg(_with_dht(bits, bytes(255)))
+    bits = [0, 0, 0, 0, 0, 0, 0, 0, 200] + [0] * 7     # 200 nine-bit codes do fit (<= 512), 3 one-bit codes never do
+    with pytest.raises(rt.B200rtError):
+        rt.decode_jpeg(_with_dht(bits, bytes(200)))    # valid table, but no frame: still an error, not a crash
+    with pytest.raises(rt.B200rtError, match="over-subscribed"):
+        rt.decode_jpeg(_with_dht([3] + [0] * 15, bytes(3)))
+    with pytest.raises(rt.B200rtError):
+        rt.decode_jpeg(b"\xff\xd8\xff\xda\x00\x02\xff\xd9")   # SOS with an empty body
+
+
+def test_mutated_streams_never_crash(rt):
+    """Byte-flip fuzzing of valid baseline and progressive streams: every outcome is an image or an error."""
+    rng = np.random.default_rng(7)
+    for kw in ({"quality": 80}, {"quality": 60, "progressive": True}, {"quality": 70, "optimize": True}):
+        good = bytearray(_encode(_picture(40, 24, 3), **kw))
+        for _ in range(150):
+            bad = bytearray(good)
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(2, len(bad)))] = int(rng.integers(0, 256))
+            try:
+                out = rt.decode_jpeg(bytes(bad))
+                assert out.ndim == 3 and out.shape[2] == 3
+            except rt.B200rtError:
+                pass
+
+
 def test_image_path_texture_is_decoded_at_finalize(rt, tmp_path):
     """TextureLoader::ImagePath(path) -> image::open(path) at SceneBuilder::finalize (loader.rs:47-60)."""
     arr = _picture(40, 20, 9)
