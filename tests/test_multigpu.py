@@ -20,6 +20,80 @@ def _free_port():
     return p
 
 
+def _strong_worker(rank, world, port, total_spp, width, out_path):
+    """ONE frame of `total_spp` samples split into contiguous sample ranges over the ranks (bench.py's strong scaling)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import shirley_raytracing_rs_b200 as rt
+    from shirley_raytracing_rs_b200.sharding import PeerFrame, sample_ranges
+    F = rt._ffi
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    scene = rt.Scene.named("random", seed=0xDEADBEEF)
+    cam = rt.default_camera(width)
+    pf = PeerFrame(cam.image_width, cam.image_height, rank)
+    sr = sample_ranges(total_spp, world)[rank]
+    rays = 0
+    for rep in range(2):
+        pf.begin_frame()
+        p = F.RenderParams(samples=sr.samples, sample_offset=sr.sample_offset, max_depth=50, seed=31, device=-1)
+        F.check(F.lib.b200rt_render_device(scene.device(rank), C.byref(cam), C.byref(p), pf.accum_ptr, None))
+        pf.combine(total_spp)
+        st = F.Stats()
+        F.check(F.lib.b200rt_render_device_finish(scene.device(rank), None, C.byref(st)))
+        rays = st.rays
+    frame = pf.frame().cpu().numpy().copy() if rank == 0 else None      # frame(): waits for every band, raises on a flag time-out
+    tot = torch.tensor([float(rays)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    if rank == 0:
+        np.savez(out_path, frame=frame, rays=tot.cpu().numpy())
+    pf.close()
+    dist.destroy_process_group()
+
+
+def test_strong_scaled_frame_equals_one_gpu_frame(tmp_path, rt, gpu_required):
+    """The BASELINE metric's frame (1200x800, 500 spp) split over two GPUs by sample ranges (250 + 250) is the frame one
+    GPU renders alone: the same (pixel, sample) streams, f32 partial sums -> at most one 8-bit level apart, same ray count."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "strong.npz")
+    mp.spawn(_strong_worker, args=(2, _free_port(), 500, 1200, out), nprocs=2, join=True)
+    got = np.load(out)
+    scene = rt.Scene.named("random", seed=0xDEADBEEF)
+    cam = rt.default_camera(1200)
+    full, st = rt.render(scene, cam, samples=500, seed=31)
+    want = rt.resolve_rgb8(full, samples=500)
+    d = np.abs(got["frame"].astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3, (d.max(), (d > 0).mean())
+    assert int(got["rays"][0]) == st.rays
+
+
+def test_bench_line_at_two_gpus(rt, gpu_required):
+    """bench.py under torchrun at N = 2 (reduced spp): one JSON line, strong scaling, the in-run correctness checks."""
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "2", "--warmup", "1", "--spp", "20", "--no-other-configs"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=540)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["config"]["spp"] == 20 and line["config"]["spp_per_gpu"] == 10
+    assert line["combine_check"] == "ok" and line["strong_check"]["max_level_diff"] <= 1
+    assert line["e2e"]["value"] > 0 and line["e2e_single_process"]["value"] > 0 and line["gpu_launches"] > 0
+    assert "frame_breakdown" in line and line["roofline"]["frac"] > 0
+
+
 def _worker(rank, world, port, spp, out_path, barrier):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
