@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_HERE, "libb200rt.so")   # B200RT_LIB: an alternative build (A/B runs of kernel variants)
 
 # ---- status codes --------------------------------------------------------------------------
 OK, EINVAL, ECUDA, ENOMEM, ESTACK, EIO = 0, -1, -2, -3, -4, -5

@@ -68,6 +68,7 @@ struct Scratch {                     // per in-flight render: counters, events, 
     cudaStream_t own_stream = nullptr;
     float4* d_accum = nullptr; size_t accum_px = 0;
     uint8_t* d_rgb = nullptr; size_t rgb_bytes = 0;
+    long long* d_fix = nullptr; size_t fix_px = 0;     // fixed-point sums of a launch whose tiles are split into sample chunks
     uint32_t launches = 0;
 };
 
@@ -314,16 +315,45 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         int rc = set_smem(kernel, plan.bytes); if (rc) return rc;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, block_threads, plan.bytes));
         if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path-tracing kernel does not fit on an SM (smem %u B, %d threads)", plan.bytes, block_threads);
-        uint32_t warps_per_block = (uint32_t)block_threads / 32;
-        uint32_t warps_needed = (a.n_tiles + a.shard_count - 1) / a.shard_count;
-        uint32_t grid = (uint32_t)(sc->sm_count * blocks_per_sm);
-        uint32_t grid_needed = (warps_needed + warps_per_block - 1) / warps_per_block;
-        if (grid_needed < grid) grid = grid_needed ? grid_needed : 1;
+        const uint32_t warps_per_block = (uint32_t)block_threads / 32;
+        const uint32_t my_tiles = (a.n_tiles + a.shard_count - 1) / a.shard_count;
+        const uint32_t full_grid = (uint32_t)(sc->sm_count * blocks_per_sm);
+        // Work granularity: a warp takes whole tiles while the frame has >= ITEMS_PER_WARP of them per resident warp;
+        // below that each tile's samples are split into `chunks` ranges (at least MIN_CHUNK_SPP samples each) so the
+        // persistent grid stays balanced to the end of the launch.  B200RT_CHUNKS=n forces a split (1 = whole tiles).
+        const uint32_t ITEMS_PER_WARP = 80, MIN_CHUNK_SPP = 14;     // measured: profiles/ (chunk sweeps at 500, 63 and 50 spp)
+        uint64_t want_items = (uint64_t)ITEMS_PER_WARP * full_grid * warps_per_block;
+        uint32_t chunks = my_tiles ? (uint32_t)std::min<uint64_t>((want_items + my_tiles - 1) / my_tiles, std::max(1u, a.samples / MIN_CHUNK_SPP)) : 1u;
+        if (int forced = env_int("B200RT_CHUNKS", 0)) chunks = (uint32_t)std::min<int64_t>(std::max(1, forced), (int64_t)a.samples);
+        if ((uint64_t)my_tiles * chunks > 0xFFFFFFF0ull) chunks = 1;      // the 32-bit work counter
+        a.chunks = chunks ? chunks : 1u;
+        a.fix = nullptr;
+        if (a.chunks > 1u) {
+            const size_t px = (size_t)W * H;
+            if (scr->fix_px < px) {
+                cudaFree(scr->d_fix); scr->d_fix = nullptr; scr->fix_px = 0;
+                cudaError_t e = cudaMalloc(&scr->d_fix, px * 3 * sizeof(long long));
+                if (e != cudaSuccess) return fail(B200RT_ENOMEM, "fixed-point accumulation buffer (%zu px): %s", px, cudaGetErrorString(e));
+                scr->fix_px = px;
+            }
+            a.fix = scr->d_fix;
+            CU(cudaMemsetAsync(scr->d_fix, 0, px * 3 * sizeof(long long), stream));
+        }
+        const uint64_t warps_needed = (uint64_t)my_tiles * a.chunks;
+        uint32_t grid = full_grid;
+        const uint64_t grid_needed = (warps_needed + warps_per_block - 1) / warps_per_block;
+        if (grid_needed < grid) grid = grid_needed ? (uint32_t)grid_needed : 1;
         CU(cudaEventRecord(scr->ev1, stream));
         kernel<<<grid, block_threads, plan.bytes, stream>>>(a);
         CU(cudaGetLastError());
-        CU(cudaEventRecord(scr->ev2, stream));
         scr->launches += 1;
+        if (a.chunks > 1u && a.row_end > a.row_begin) {
+            dim3 fb(128, 1), fg((W + 127) / 128, a.row_end - a.row_begin);
+            finalize_kernel<<<fg, fb, 0, stream>>>(a);
+            CU(cudaGetLastError());
+            scr->launches += 1;
+        }
+        CU(cudaEventRecord(scr->ev2, stream));
         return B200RT_OK;
     };
     int rc;
@@ -602,6 +632,7 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     sc->ds.tex = reinterpret_cast<const TexRec*>(dbase + off_tex);
     sc->ds.images = reinterpret_cast<const ImageRec*>(dbase + off_images);
     sc->ds.perlin = d->n_perlin ? reinterpret_cast<const PerlinRec*>(dbase + off_perlin) : nullptr;
+    sc->ds.n_perlin = d->n_perlin;
     sc->ds.n_top_prims = ds_top.n_top_prims;
     for (int k = 0; k < 7; ++k) sc->ds.top_prims[k] = ds_top.top_prims[k];
     sc->box_pad = pad; sc->max_abs_coord = max_abs;

@@ -35,6 +35,8 @@ struct RenderArgs {
     uint32_t tiles_x, tile_row0, n_tiles;       // tile grid covering [row_begin, row_end)
     uint32_t shard_count, shard_index;
     uint32_t accumulate;
+    uint32_t chunks;                            // work item = (tile, one of `chunks` contiguous sample ranges); > 1: sums go to `fix`
+    long long* fix;                             // chunks > 1: per-pixel 2^-32 fixed-point sums [H][W][3] in global memory (finalize_kernel converts)
     uint32_t trav_threshold;                    // leave the traversal loop when fewer lanes than this still traverse
     float4* accum;
     Counters* counters;
@@ -82,14 +84,27 @@ constexpr uint32_t RAYQ_SLOTS = 32, RAYQ_FIELDS = 9;   // v2: o, d, RNG state + 
 // carry the NaN into the pixel, which to_image writes as 0).  Each channel of a finite sample is clamped to +-`lim` =
 // 2e9 / samples-per-call, so a pixel's 2^-32 fixed-point sum (63 bits: |sum| < 2^31 = 2.1e9) cannot wrap whatever the
 // emitters' strength; a clamped sample still saturates the pixel (to_image clips the mean at 1).
+// The 64-bit add is two native 32-bit shared-memory atomics (low word with the old value returned, then the high word
+// plus the carry, skipped when both are zero — the usual case: samples below 1.0 have no high word): integer adds
+// commute and every carry is counted exactly once, so the sum is the same 64-bit integer whatever the order.
+// (atomicAdd on a 64-bit shared word compiles to a compare-and-swap loop, ATOMS.CAST.SPIN.64: 3.5 % of the kernel's
+// issue slots at 6-10 lanes.)
+__device__ __forceinline__ void acc_add64(uint32_t word_addr, long long x) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)((unsigned long long)x >> 32);
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(word_addr), "r"(lo) : "memory");
+    const uint32_t up = hi + ((old + lo) < lo ? 1u : 0u);
+    if (up) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(word_addr + 4u), "r"(up) : "memory");
+}
 __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v, float lim) {
     const float S = 4294967296.0f;
     // one test: any NaN or infinity makes the sum NaN or infinite (radiance is non-negative; the quarter keeps a finite triple finite)
     if (fabsf(fmaf(v.x, 0.25f, fmaf(v.y, 0.25f, v.z * 0.25f))) <= 3.0e38f) {
         v.x = fminf(fmaxf(v.x, -lim), lim); v.y = fminf(fmaxf(v.y, -lim), lim); v.z = fminf(fmaxf(v.z, -lim), lim);
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 0), (unsigned long long)__float2ll_rn(v.x * S));
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 1), (unsigned long long)__float2ll_rn(v.y * S));
-        atomicAdd(reinterpret_cast<unsigned long long*>(acc + pixel * 3 + 2), (unsigned long long)__float2ll_rn(v.z * S));
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(acc + pixel * 3);
+        acc_add64(a0, __float2ll_rn(v.x * S));
+        acc_add64(a0 + 8u, __float2ll_rn(v.y * S));
+        acc_add64(a0 + 16u, __float2ll_rn(v.z * S));
     }
 }
 
@@ -129,6 +144,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                      + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
     const float T_MIN = 0.001f;                      // render.rs:31
     const bool has_perlin = a.scene.perlin != nullptr;
+    // (the Perlin tables stay in global memory behind L1: a shared-memory copy reached through generic loads measured 0.4 % slower)
+    const PerlinRec* perlin_tables = a.scene.perlin;
     const float sample_lim = 2.0e9f / (float)a.samples;   // acc_add: the per-call fixed-point sum cannot wrap
 
     unsigned long long w_rays = 0, w_paths = 0, w_exh = 0, w_nodes = 0, w_prims = 0;
@@ -142,8 +159,14 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         unsigned int j = 0;
         if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
         j = __shfl_sync(FULL, j, 0);
-        unsigned long long t64 = (unsigned long long)j * a.shard_count + a.shard_index;
+        // Work item j = (tile j / chunks, sample range j % chunks): a tile's samples are split over several warps when the
+        // frame has too few tiles to balance the grid (1200x800 at 500 spp is 10.5 whole tiles per warp: the kernel ran 18 %
+        // below its rate on frames with 4x the tiles).  Bottom rows first either way.
+        const uint32_t chunk = a.chunks > 1u ? j % a.chunks : 0u;
+        unsigned long long t64 = (unsigned long long)(a.chunks > 1u ? j / a.chunks : j) * a.shard_count + a.shard_index;
         if (t64 >= a.n_tiles) break;
+        const uint32_t s_begin = (uint32_t)((unsigned long long)a.samples * chunk / a.chunks);
+        const uint32_t s_count = (uint32_t)((unsigned long long)a.samples * (chunk + 1u) / a.chunks) - s_begin;
         uint32_t t = (uint32_t)t64;
         uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
@@ -154,7 +177,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         // (with lane = pixel, 17 % of the lanes sat out of samples at tile ends).
         const unsigned valid_mask = __ballot_sync(FULL, valid);
         const uint32_t nv = (uint32_t)__popc(valid_mask);
-        const uint32_t n_items = a.samples * nv;
+        const uint32_t n_items = s_count * nv;
         uint32_t next_item = 0;          // next work-list item to generate
         uint32_t q_head = 0, q_count = 0;  // the warp's ring of generated primary rays
         for (int k = lane; k < 96; k += 32) wacc[k] = 0;
@@ -196,7 +219,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             }
             float turb = 0.0f;
             if (has_perlin && __any_sync(FULL, hit && sp_.tex.need_perlin))   // warp-uniform: skip the call when no lane asks
-                turb = coop_turbulence(a.scene.perlin, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
+                turb = coop_turbulence(perlin_tables, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
             if (hit) {
                 float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
                 ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                     uint32_t qpl = (nv == 32u) ? kth : (uint32_t)__fns(valid_mask, 0, (int)kth + 1);
                     uint32_t px = px0 + (qpl & (TILE_W - 1)), py = py0 + (qpl >> 3);
                     Rng qr;
-                    qr.init(a.keys, py * a.cam.width + px, a.sample_offset + sidx);
+                    qr.init(a.keys, py * a.cam.width + px, a.sample_offset + s_begin + sidx);
                     float jx = (float)px + qr.gen();
                     float jy = (float)py + qr.gen();
                     float3 qo, qd;
@@ -295,11 +318,20 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         }
         __syncwarp();
         if (valid) {
-            const float inv = 1.0f / 4294967296.0f;
-            float4* dst = a.accum + (my_py * a.cam.width + my_px);
-            float4 v = make_float4((float)wacc[lane * 3 + 0] * inv, (float)wacc[lane * 3 + 1] * inv, (float)wacc[lane * 3 + 2] * inv, (float)a.samples);
-            if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
+            if (a.chunks > 1u) {
+                // several warps hold partial sums of this pixel: exact 64-bit integer adds in global memory (native RED.ADD.64),
+                // so the total — and the float finalize_kernel derives from it — is the same whatever the split or the order
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(a.fix) + ((size_t)my_py * a.cam.width + my_px) * 3;
+                atomicAdd(f + 0, (unsigned long long)wacc[lane * 3 + 0]);
+                atomicAdd(f + 1, (unsigned long long)wacc[lane * 3 + 1]);
+                atomicAdd(f + 2, (unsigned long long)wacc[lane * 3 + 2]);
+            } else {
+                const float inv = 1.0f / 4294967296.0f;
+                float4* dst = a.accum + (my_py * a.cam.width + my_px);
+                float4 v = make_float4((float)wacc[lane * 3 + 0] * inv, (float)wacc[lane * 3 + 1] * inv, (float)wacc[lane * 3 + 2] * inv, (float)a.samples);
+                if (a.accumulate) { float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *dst = v;
+            }
         }
         __syncwarp();
         w_rays += lane == 0 ? nrays : 0u; w_exh += nexh; w_paths += lane == 0 ? n_items : 0u;   // every work-list item became one path
@@ -327,5 +359,19 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
     }
 }
 
+
+// chunks > 1: fixed-point sums -> the float4 accumulation buffer, for exactly the pixels the launch rendered
+// (same arithmetic as the kernel's own tile write-back, so the result does not depend on `chunks`).
+__global__ void finalize_kernel(const __grid_constant__ RenderArgs a) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = a.row_begin + blockIdx.y;
+    if (x >= a.cam.width || y >= a.row_end) return;
+    const uint32_t t = (y / TILE_H - a.tile_row0) * a.tiles_x + x / TILE_W;
+    if (t % a.shard_count != a.shard_index) return;
+    const size_t p = (size_t)y * a.cam.width + x;
+    const float inv = 1.0f / 4294967296.0f;
+    float4 v = make_float4((float)a.fix[p * 3 + 0] * inv, (float)a.fix[p * 3 + 1] * inv, (float)a.fix[p * 3 + 2] * inv, (float)a.samples);
+    if (a.accumulate) { float4 o = a.accum[p]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    a.accum[p] = v;
+}
 
 }  // namespace b200rt

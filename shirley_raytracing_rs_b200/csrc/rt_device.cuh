@@ -54,7 +54,7 @@ struct DeviceScene {
     const TexRec* tex;
     const ImageRec* images;
     const PerlinRec* perlin;
-    uint32_t n_nodes, n_prims, n_tex, bvh_depth;
+    uint32_t n_nodes, n_prims, n_tex, bvh_depth, n_perlin;
     uint32_t sky_kind; float sky_r, sky_g, sky_b;
     // Primitives whose box covers most of the scene (the Weekend ground rect and its
     // dielectric coat box) are not BVH leaves: nearly every ray meets them, so they are
