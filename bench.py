@@ -59,6 +59,8 @@ sys.path.insert(0, ROOT)
 
 WIDTH, SPP, DEPTH, SCENE_SEED = 1200, 500, 50, 0xDEADBEEF
 WORKLOAD = "weekend_final_scene_1200x800_500spp_depth50"
+# ncu --set full of the C4 launches (scripts/profile_c4.py; profiles/r02_c4_metrics.md): bytes per 64-spp launch
+C4_NCU = {"lts_1e6": 328850676384, "dram_1e6": 438811136, "lts_1e5": 247191012224, "dram_1e5": 380317440}
 METRIC = "Mrays/s, Weekend final scene 1200x800 500spp (ms/frame in ms_per_step)"
 
 
@@ -557,6 +559,7 @@ def other_configs(rt, sharding, rank, world, local_rank, dev, stream, sptr, fp32
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    l2_peak = rt.read_peak(48 << 20, local_rank)          # GB/s, float4 loads over a 48 MiB (L2-resident) buffer, measured live
 
     def run(name, scene, cam, total_spp, mode):
         W, H = cam.image_width, cam.image_height
@@ -619,11 +622,18 @@ def other_configs(rt, sharding, rank, world, local_rank, dev, stream, sptr, fp32
                    "roofline": {"bound": "fp32-issue", "achieved": rps * opr / 1e12, "peak": fp32_peak * world / 1e12, "unit": "Tlane-op/s",
                                 "frac": rps * opr / (fp32_peak * world), "ops_per_ray": opr}}
             if not in_smem:
-                # the tree lives in global memory: algorithmic bytes per ray x rays/s against HBM (the tree is mostly L2-resident,
-                # so this is the traffic L1 + L2 + HBM serve together; profiles/ has the lts__t_bytes / dram__bytes split from ncu)
-                out["roofline_bytes"] = {"bound": "hbm", "achieved": rps * bpr / 1e9, "peak": hbm_peak * world, "unit": "GB/s", "frac": rps * bpr / 1e9 / (hbm_peak * world),
-                                         "bytes_per_ray": bpr, "traffic": None,
-                                         "note": "algorithmic node + primitive bytes per ray; served by L1/L2 (tree mostly cache-resident), DRAM traffic per launch in profiles/"}
+                # The tree lives in global memory and is served mostly by L1 and L2 (ncu, profiles/r02_c4_metrics.md: L1 hit rate
+                # ~92 %, L2 ~80-87 %): algorithmic node + primitive bytes per ray x rays/s against the L2 read ceiling measured
+                # live (b200rt_read_peak over 48 MiB) and against the HBM figure of MEASURED_PEAKS.json.  `traffic` = what one
+                # 64-spp launch of this kernel moved at L2 (lts__t_bytes.sum) and at DRAM (dram__bytes_read + write), from ncu.
+                ncu = {"c4_1e6": {"lts_bytes": C4_NCU.get("lts_1e6"), "dram_bytes": C4_NCU.get("dram_1e6")}, "c4_1e5": {"lts_bytes": C4_NCU.get("lts_1e5"), "dram_bytes": C4_NCU.get("dram_1e5")}}
+                key = "c4_1e6" if info.n_prims > 500000 else "c4_1e5"
+                out["roofline_bytes"] = {"bound": "l2", "achieved": rps * bpr / 1e9, "peak": l2_peak * world, "unit": "GB/s", "frac": rps * bpr / 1e9 / (l2_peak * world),
+                                         "bytes_per_ray": bpr, "peak_source": "b200rt_read_peak(48 MiB) measured live (L2-resident float4 reads)",
+                                         "hbm": {"peak": hbm_peak * world, "frac": rps * bpr / 1e9 / (hbm_peak * world), "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+                                         "traffic": ncu[key]["dram_bytes"], "traffic_l2": ncu[key]["lts_bytes"],
+                                         "traffic_unit": "bytes per 64-spp single-GPU launch (ncu --set full, profiles/r02_c4_metrics.md): dram__bytes_read.sum + dram__bytes_write.sum; traffic_l2 = lts__t_bytes.sum",
+                                         "note": "algorithmic bytes (64 B per node visit, 16 B per primitive test, 32 B material per ray) are mostly L1 hits; L2 and DRAM see the miss traffic"}
         if pf is not None:
             pf.close()
         scene.close()

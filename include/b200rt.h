@@ -320,7 +320,8 @@ void b200rt_free(void* p);
 
 /* K1: Scene/BboxTree::hit_workspace over a ray array (bvh/bbox_tree.rs:56-91).
  * ids[i] = hit id or -1; hits may be NULL. Interval is inclusive on both ends like
- * sphere.rs:41-46; among exactly equal t the highest id wins. */
+ * sphere.rs:41-46; among exactly equal t the highest id wins.  stats (may be NULL): rays and kernel_ms always;
+ * node_visits / prim_tests only when `hits` is requested too (ids-only calls run without the counters). */
 int  b200rt_closest_hit(const B200rtScene* scene, const B200rtRay* rays, size_t n,
                         float t_min, float t_max, int32_t* ids, B200rtHit* hits,
                         B200rtStats* stats);
@@ -354,6 +355,10 @@ int  b200rt_rng_uniforms(uint64_t seed, uint32_t a, uint32_t b, size_t n, float*
 /* Measured FP32 issue ceiling of the device: FFMA-chain microbenchmark; returns
  * lane-instructions per second (FMA counted once) in *out. Roofline denominator. */
 int  b200rt_fp32_peak(int device, double* lane_instr_per_s);
+/* Measured read bandwidth (GB/s) over a device buffer of `bytes` (>= 1 MiB), float4 loads through L2 (.cg): a buffer well
+ * inside the L2 (e.g. 48 MiB) gives the L2 ceiling, a multi-GB one the HBM ceiling.  Roofline denominators for scenes whose
+ * BVH lives in global memory. */
+int  b200rt_read_peak(int device, size_t bytes, double* gb_per_s);
 
 #ifdef __cplusplus
 }

@@ -150,6 +150,7 @@ SIGNATURES = {
     "b200rt_texture_value": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200rt_rng_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_int]),
     "b200rt_fp32_peak": (C.c_int, [C.c_int, _P(C.c_double)]),
+    "b200rt_read_peak": (C.c_int, [C.c_int, C.c_size_t, _P(C.c_double)]),
     # b200rt_host.h
     "b200rt_host_last_error": (C.c_char_p, []),
     "b200rt_host_scene_from_json": (C.c_int, [C.c_char_p, C.c_size_t, C.c_uint64, _P(C.c_void_p)]),

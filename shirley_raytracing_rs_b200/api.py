@@ -442,5 +442,12 @@ def fp32_peak(device: int = -1) -> float:
     return v.value
 
 
+def read_peak(nbytes: int, device: int = -1) -> float:
+    """Measured read bandwidth in GB/s over a buffer of `nbytes` (48 MiB: the L2 ceiling; 4 GiB: the HBM ceiling)."""
+    v = C.c_double()
+    F.check(lib.b200rt_read_peak(device, nbytes, C.byref(v)))
+    return v.value
+
+
 def device_count() -> int:
     return lib.b200rt_device_count()

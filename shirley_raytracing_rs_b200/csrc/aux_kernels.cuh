@@ -34,8 +34,7 @@ __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constan
         float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
         ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
         ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
-        ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
-        Closest c; c.t = a.t_max; c.code = -1; c.face = 0;
+        Closest c; c.t = a.t_max; c.code = -1;
 #pragma unroll 1
         for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
             if (COUNT) tc.prims++;
@@ -48,7 +47,7 @@ __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constan
             if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
         }
         ++nr;
-        int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_LEAF_ID_MASK);
+        int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_CODE_ID_MASK);
         a.ids[i] = id;
         if (a.hits) {
             B200rtHit out;
@@ -288,5 +287,18 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+
+// Read-bandwidth probe: every thread sums float4 loads over a buffer, several passes.  A buffer well inside the 126 MB L2
+// measures the L2 ceiling, a much larger one the HBM ceiling (roofline denominators for scenes whose tree lives in global memory).
+__global__ void __launch_bounds__(256) read_peak_kernel(const float4* __restrict__ buf, size_t n4, int passes, float* out) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; ++p)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 v = __ldcg(buf + i);                       // .cg: L2 only, so the figure is not an L1 hit rate
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.678f) out[0] = acc.x;     // keeps the loads alive
+}
 
 }  // namespace b200rt

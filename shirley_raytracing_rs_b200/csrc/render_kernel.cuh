@@ -185,7 +185,6 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
         uint32_t nrays = 0, nexh = 0;   // nrays: warp total (same value in every lane), nexh: per lane
         TravCounters tc; tc.nodes = 0; tc.prims = 0;
-        bool alive = false;
         Rng rng; rng.state = 0; rng.inc = 1;
         RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
@@ -193,7 +192,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         int node = B200RT_TRAV_DONE;
         const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
         uint32_t top_sp = stack_s + BLK * 4;   // shared-window address of the next free slot of this lane's stack column
-        Closest c; c.t = INFINITY; c.code = -1; c.face = 0;
+        Closest c; c.t = INFINITY; c.code = -1;
         stack[0] = B200RT_TRAV_DONE;     // sentinel: popping it ends a traversal (trav_inner_s)
 
         // One outer iteration = shade the lanes whose traversal finished, hand new paths to the
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         // set-up + up-front primitive code, run at ~30 lanes instead of twice at 6 and 18), traverse.
         for (;;) {
             // ---- shade: ray_color's loop body, render.rs:31-46 ----
-            bool fin = alive && node == B200RT_TRAV_DONE;
+            bool fin = depth != 0u && node == B200RT_TRAV_DONE;     // a lane holds a path while depth != 0
             if (COUNT) { d0 += 1; d5 += __popc(__ballot_sync(FULL, fin)); }
             bool hit = fin && c.code >= 0;
             bool done = false, setup = false;
@@ -229,13 +228,13 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                     else { ray.o = so.o; ray.d = so.d; setup = true; }
                 }
             }
-            if (done) { acc_add(wacc, pl, emit, sample_lim); alive = false; }
+            if (done) { acc_add(wacc, pl, emit, sample_lim); depth = 0; }
 
             // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
             // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG
             // keying, jitter, lens rejection loop, Camera::pixel_ray) and handed out to the ~6 lanes
             // per iteration whose path ended; generating them on demand ran that code at 6 lanes.
-            unsigned want_m = __ballot_sync(FULL, !alive);
+            unsigned want_m = __ballot_sync(FULL, depth == 0u);
             const uint32_t want = (uint32_t)__popc(want_m);
             if (q_count < want && next_item < n_items) {           // warp-uniform
                 __syncwarp();
@@ -263,8 +262,8 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 __syncwarp();
             }
             const uint32_t rank = (uint32_t)__popc(want_m & lt);
-            bool regen = !alive && rank < q_count;
-            if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, !alive && !regen)); }
+            bool regen = depth == 0u && rank < q_count;
+            if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, depth == 0u && !regen)); }
             if (regen) {
                 uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);
                 ray.o = f3(__uint_as_float(rayq[0 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[1 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[2 * RAYQ_SLOTS + slot]));
@@ -272,15 +271,14 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot]; pl = rayq[8 * RAYQ_SLOTS + slot];
                 atten = f3(1, 1, 1); emit = f3(0, 0, 0);
                 depth = a.max_depth;
-                alive = depth > 0;
-                setup = alive;
+                setup = depth != 0u;
             }
             {
                 uint32_t taken = min(want, q_count);
                 q_head = (q_head + taken) & (RAYQ_SLOTS - 1); q_count -= taken;
             }
-            if (!__any_sync(FULL, alive)) break;
-            if (COUNT) d1 += __popc(__ballot_sync(FULL, alive));
+            if (!__any_sync(FULL, depth != 0u)) break;
+            if (COUNT) d1 += __popc(__ballot_sync(FULL, depth != 0u));
 
             // ---- new segment: per-ray constants, then the scene-spanning primitives ----
             if (setup) {
@@ -289,8 +287,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
                 ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
                 ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
-                ray.a = fmaf(ray.d.z, ray.d.z, fmaf(ray.d.y, ray.d.y, __fmul_rn(ray.d.x, ray.d.x)));
-                c.t = INFINITY; c.code = -1; c.face = 0;
+                c.t = INFINITY; c.code = -1;
                 // the list is indexed in the kernel parameters (constant bank): a register copy indexed by a
                 // loop counter would live in local memory
 #pragma unroll 1

@@ -28,6 +28,9 @@ struct BvhNode { float4 q0, q1, q2, q3; };
 
 #define B200RT_LEAF_TYPE_SHIFT 28
 #define B200RT_LEAF_ID_MASK 0x0FFFFFFFu
+// Closest::code = (type << 28) | (box face / 2 << 26) | id: the face of a RectBox hit rides in two spare bits (ids stay below 2^26)
+#define B200RT_CODE_ID_MASK 0x03FFFFFFu
+#define B200RT_CODE_FACE_SHIFT 26
 #define B200RT_EMPTY_LEAF ((int)0x80000000)   // ~0x7FFFFFFF: never produced for a real prim
 
 // Geometry record per hit id, 32 B = 2 x float4:
@@ -179,14 +182,12 @@ struct RayF {
                         // only cull and are padded).  Primitive tests take their own IEEE reciprocals so
                         // they stay bit-reproducible on the CPU.
     float3 ood;         // o * inv, for the one-FMA-per-plane slab test
-    float a;            // d.d
 };
 __device__ __forceinline__ RayF make_ray(float3 o, float3 d) {
     RayF r;
     r.o = o; r.d = d;
     r.inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
     r.ood = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
-    r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
     return r;
 }
 // The slab tests take a reciprocal clamped to +-1e18: with an infinite one (direction component exactly 0) the
@@ -199,7 +200,6 @@ __device__ __forceinline__ RayF make_ray_shade(float3 o, float3 d) {
     RayF r;
     r.o = o; r.d = d;
     r.inv = f3(0.f, 0.f, 0.f); r.ood = r.inv;
-    r.a = fmaf(d.z, d.z, fmaf(d.y, d.y, __fmul_rn(d.x, d.x)));
     return r;
 }
 
@@ -251,13 +251,13 @@ __device__ __forceinline__ void aabb_center(const RayF& r, float cx, float cy, f
 // ------------------------------------------------------------------------------------------
 struct Closest {
     float t;       // current closest distance (starts at t_max)
-    int code;      // (type << 28) | id of the closest prim, -1 = none
-    int face;      // box only: which of the 6 rects (rect.rs:149-154 order) was hit
+    int code;      // (type << 28) | (face / 2 << 26) | id of the closest prim, -1 = none; face (box only) = which of the 6 rects
+                   // (rect.rs:149-154 order) was hit, as the first index of its pair: 0 (z), 2 (x), 4 (y)
 };
 
 __device__ __forceinline__ bool accept_t(float t, float t_min, const Closest& c, int id) {
     // NaN-safe: a NaN root is rejected.
-    return (t >= t_min) && (t < c.t || (t == c.t && (c.code < 0 || id > (int)(c.code & B200RT_LEAF_ID_MASK))));
+    return (t >= t_min) && (t < c.t || (t == c.t && (c.code < 0 || id > (int)(c.code & B200RT_CODE_ID_MASK))));
 }
 
 // Sphere::hit (geometry/sphere.rs:29-52).  Same roots as the reference's textbook
@@ -267,14 +267,15 @@ __device__ __forceinline__ bool accept_t(float t, float t_min, const Closest& c,
 __device__ __forceinline__ bool sphere_roots(const RayF& r, float4 s, float* root_lo, float* root_hi) {
     float ocx = __fsub_rn(r.o.x, s.x), ocy = __fsub_rn(r.o.y, s.y), ocz = __fsub_rn(r.o.z, s.z);
     float bp = -fmaf(ocz, r.d.z, fmaf(ocy, r.d.y, __fmul_rn(ocx, r.d.x)));   // -half_b
-    float inv_a = rcp_exact(r.a);
+    const float a = fmaf(r.d.z, r.d.z, fmaf(r.d.y, r.d.y, __fmul_rn(r.d.x, r.d.x)));   // d.d (sphere.rs:31), taken here: one live register fewer across the traversal
+    float inv_a = rcp_exact(a);
     float q = __fmul_rn(bp, inv_a);
     float lx = fmaf(q, r.d.x, ocx), ly = fmaf(q, r.d.y, ocy), lz = fmaf(q, r.d.z, ocz);
     float l2 = fmaf(lz, lz, fmaf(ly, ly, __fmul_rn(lx, lx)));
     float r2 = __fmul_rn(s.w, s.w);
     float delta = __fsub_rn(r2, l2);               // discriminant / a
     if (delta < 0.0f) return false;                // sphere.rs:35-37
-    float sq = __fsqrt_rn(__fmul_rn(delta, r.a));  // sqrt(discriminant)
+    float sq = __fsqrt_rn(__fmul_rn(delta, a));  // sqrt(discriminant)
     float qq = __fadd_rn(bp, copysignf(sq, bp));
     float c = __fsub_rn(fmaf(ocz, ocz, fmaf(ocy, ocy, __fmul_rn(ocx, ocx))), r2);
     float r0 = __fdiv_rn(c, qq);
@@ -344,8 +345,8 @@ __device__ __forceinline__ void hit_box(const RayF& r, float4 lo, float4 hi, int
     if (!accept_t(t, t_min, c, id)) return;
     float ty = entering ? ny : fy, tx = entering ? nx : fx;
     c.t = t;
-    c.face = (ty == t) ? 4 : ((tx == t) ? 2 : 0);
-    c.code = (int)((B200RT_PRIM_BOX << B200RT_LEAF_TYPE_SHIFT) | (uint32_t)id);
+    const uint32_t half_face = (ty == t) ? 2u : ((tx == t) ? 1u : 0u);
+    c.code = (int)((B200RT_PRIM_BOX << B200RT_LEAF_TYPE_SHIFT) | (half_face << B200RT_CODE_FACE_SHIFT) | (uint32_t)id);
 }
 
 // GeometricObject::hit dispatch (geometry/object.rs:44-58)
@@ -464,8 +465,8 @@ __device__ __forceinline__ HitRec make_hit(const RayF& r, const Acc& acc, const 
     h.has_uv = false; h.uv_u = 0.f; h.uv_v = 0.f;
     uint32_t code = (uint32_t)c.code;
     h.type = code >> B200RT_LEAF_TYPE_SHIFT;
-    h.id = (int)(code & B200RT_LEAF_ID_MASK);
-    h.face = c.face;
+    h.id = (int)(code & B200RT_CODE_ID_MASK);
+    h.face = (int)((code >> B200RT_CODE_FACE_SHIFT) & 3u) << 1;
     h.t = c.t;
     h.p = fma3(c.t, r.d, r.o);                            // Ray::at, vec3.rs:253
     if (h.type == B200RT_PRIM_SPHERE) {
@@ -477,7 +478,7 @@ __device__ __forceinline__ HitRec make_hit(const RayF& r, const Acc& acc, const 
         h.n_out = f3(__fmul_rn(hp.x, inv_r), __fmul_rn(hp.y, inv_r), __fmul_rn(hp.z, inv_r));
     } else {
         int dn;
-        if (h.type == B200RT_PRIM_BOX) dn = (c.face < 2) ? 2 : (c.face < 4 ? 0 : 1);
+        if (h.type == B200RT_PRIM_BOX) dn = (h.face < 2) ? 2 : (h.face < 4 ? 0 : 1);
         else { int d1, d2; rect_axes(h.type, d1, d2); dn = 3 - d1 - d2; }
         h.n_out = f3(dn == 0 ? 1.0f : 0.0f, dn == 1 ? 1.0f : 0.0f, dn == 2 ? 1.0f : 0.0f);   // rect.rs:75-76
     }
@@ -729,7 +730,7 @@ __device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h,
         return out;
     }
     if (m.kind == B200RT_MAT_FAIRY_LIGHT) {                             // lighting.rs:59-66 then :43-57
-        float scale = -dot(h.n, r.d) * rsqrtf(r.a);
+        float scale = -dot(h.n, r.d) * rsqrtf(fmaf(r.d.z, r.d.z, fmaf(r.d.y, r.d.y, __fmul_rn(r.d.x, r.d.x))));
         emit = emit + atten * (a * scale);
         a = unit(a);
     }
