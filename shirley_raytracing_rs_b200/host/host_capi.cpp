@@ -90,7 +90,7 @@ int b200rt_host_decode_jpeg(const uint8_t* data, size_t size, uint32_t* width, u
     *rgb8 = nullptr;
     try {
         // image::load_from_memory sniffs the format: JPEG or PNG here
-        scene::ImageData img = (size >= 8 && data[0] == 0x89 && data[1] == 'P') ? scene::decode_png(data, size) : scene::decode_jpeg(data, size);
+        scene::ImageData img = scene::decode_any(data, size);
         uint8_t* buf = (uint8_t*)malloc(img.rgb.size() ? img.rgb.size() : 1);
         if (!buf) return host_fail(B200RT_ENOMEM, "out of memory");
         memcpy(buf, img.rgb.data(), img.rgb.size());

@@ -126,6 +126,9 @@ ImageData decode_jpeg(const uint8_t* data, size_t size);
 ImageData load_jpeg_file(const std::string& path);
 // PNG -> RGB8 (png_decoder.cpp) and the format-sniffing loader `image::open` corresponds to.
 ImageData decode_png(const uint8_t* data, size_t size);
+ImageData decode_bmp(const uint8_t* data, size_t size);     // uncompressed 1/4/8/24/32-bit
+ImageData decode_pnm(const uint8_t* data, size_t size);     // P2 P3 P5 P6
+ImageData decode_any(const uint8_t* data, size_t size);     // sniffs the format like image::load_from_memory
 ImageData load_image_file(const std::string& path);
 
 // The flattened scene: owns the SoA arrays `desc` points into.
