@@ -35,14 +35,4 @@ for G in (158, 500):
     print(f"  (host scene generation + flatten {th:.2f} s)")
     run(f"C4 scaled G={G}", s, cam, max(1, int(64 * scale)), f"c4_scaled_{G}.png")
 
-# K1 alone — the BVH-only workload of the reference's criterion bench (benches/my_benchmark.rs:35-75): a (2s)^3
-# lattice of jittered log-normal spheres, random origins in the cube, uniform directions
-for side in (8, 32, 64):
-    s = rt.Scene.named("lattice", seed=0xDEADBEEF, param=side)
-    n = 4_000_000
-    g = np.random.default_rng(1)
-    d = g.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
-    rays = np.concatenate([g.uniform(-side, side, size=(n, 3)), d], axis=1).astype(np.float32)
-    rt.closest_hit(s, rays[:1000])
-    ids, _, st = rt.closest_hit(s, rays, want_hits=False)
-    print(f"K1 lattice side {side}: {s.desc.contents.n_prims} spheres, {n} rays: kernel {st.kernel_ms:.2f} ms  {n / st.kernel_ms / 1e3:.0f} Mrays/s  hit fraction {(ids >= 0).mean():.3f}", flush=True)
+# K1 alone (the criterion-shaped BVH microbenchmark): scripts/k1_microbench.py

@@ -12,11 +12,16 @@ struct HitArgs {
     DeviceScene scene; SmemPlan plan;
     const B200rtRay* rays; size_t n; float t_min, t_max;
     int32_t* ids; B200rtHit* hits; Counters* counters;
+    unsigned long long* next_ray;      // the global ray counter the persistent warps draw from
 };
 
 // K1 runs the SAME traversal code as the render kernel (per-segment set-up with shared IEEE reciprocals, up-front
 // primitives, trav_inner_s / trav_leaf_s over the sentinel stack; FAST = centre/half-extent boxes) so that the
 // bit-exact id / t / normal parity tests exercise the product's traversal, not a parity-only twin.
+// Like the render kernel it is persistent and refills lanes: a warp takes rays from a global counter, every lane
+// traverses until it holds a leaf, the held leaves are tested together, and as soon as fewer than `refill` lanes
+// still traverse, the finished lanes store their results and take new rays (one thread per ray and a loop until the
+// warp's slowest ray ends ran at 129-314 Mrays/s on the criterion-shaped lattice: the lanes idled).
 template <class Acc, bool COUNT, bool FAST>
 __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constant__ HitArgs a) {
     extern __shared__ float4 smem[];
@@ -25,43 +30,71 @@ __global__ void __launch_bounds__(BLOCK) closest_hit_kernel(const __grid_constan
     int* stack = stack_base + threadIdx.x;
     stack[0] = B200RT_TRAV_DONE;
     const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t refill = 12;                         // leave the traversal loop below this many traversing lanes
     TravCounters tc; tc.nodes = 0; tc.prims = 0;
     unsigned long long nr = 0;
-    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < a.n; i += (size_t)gridDim.x * BLOCK) {
-        B200rtRay in = a.rays[i];
-        RayF ray;
-        ray.o = f3(in.ox, in.oy, in.oz); ray.d = f3(in.dx, in.dy, in.dz);
-        float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
-        ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
-        ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
-        Closest c; c.t = a.t_max; c.code = -1;
-#pragma unroll 1
-        for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
-            if (COUNT) tc.prims++;
-            hit_leaf(ray, acc, a.scene.top_prims[k], a.t_min, c, &inv_e);
+    long long mine = -1;                                // index of the ray this lane holds, -1 = none
+    bool exhausted = false;                             // warp-uniform: the ray counter ran past the array
+    RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
+    Closest c; c.t = a.t_max; c.code = -1;
+    int node = B200RT_TRAV_DONE;
+    uint32_t top_sp = stack_s + BLOCK * 4;
+    for (;;) {
+        // ---- store finished rays ----
+        if (mine >= 0 && node == B200RT_TRAV_DONE) {
+            ++nr;
+            int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_CODE_ID_MASK);
+            a.ids[mine] = id;
+            if (a.hits) {
+                B200rtHit out;
+                memset(&out, 0, sizeof out);
+                out.id = id;
+                if (id >= 0) {
+                    HitRec h = make_hit(ray, acc, c);
+                    float u, v;
+                    hit_uv(h, acc, &u, &v);
+                    out.t = h.t; out.p[0] = h.p.x; out.p[1] = h.p.y; out.p[2] = h.p.z;
+                    out.n[0] = h.n.x; out.n[1] = h.n.y; out.n[2] = h.n.z;
+                    out.u = u; out.v = v; out.front_face = h.front ? 1 : 0;
+                }
+                a.hits[mine] = out;
+            }
+            mine = -1;
         }
-        int node = 0;
-        uint32_t top_sp = stack_s + BLOCK * 4;
-        while (node != B200RT_TRAV_DONE) {
+        // ---- refill: the free lanes take the next rays ----
+        const unsigned want_m = __ballot_sync(FULL, mine < 0);
+        if (want_m && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)__popc(want_m));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= a.n) exhausted = true;
+            const unsigned long long i = base + (unsigned long long)__popc(want_m & lt);
+            if (mine < 0 && i < a.n) {
+                mine = (long long)i;
+                B200rtRay in = a.rays[i];
+                ray.o = f3(in.ox, in.oy, in.oz); ray.d = f3(in.dx, in.dy, in.dz);
+                float3 inv_e = f3(__frcp_rn(ray.d.x), __frcp_rn(ray.d.y), __frcp_rn(ray.d.z));
+                ray.inv = FAST ? f3(clamp_inv(inv_e.x), clamp_inv(inv_e.y), clamp_inv(inv_e.z)) : inv_e;
+                ray.ood = f3(ray.o.x * ray.inv.x, ray.o.y * ray.inv.y, ray.o.z * ray.inv.z);
+                c.t = a.t_max; c.code = -1;
+#pragma unroll 1
+                for (uint32_t k = 0; k < a.scene.n_top_prims; ++k) {
+                    if (COUNT) tc.prims++;
+                    hit_leaf(ray, acc, a.scene.top_prims[k], a.t_min, c, &inv_e);
+                }
+                node = 0; top_sp = stack_s + BLOCK * 4;
+            }
+        }
+        if (!__any_sync(FULL, mine >= 0)) break;
+        // ---- traverse ----
+        for (;;) {
             while (node >= 0 && node != B200RT_TRAV_DONE) trav_inner_s<COUNT, FAST>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
             if (node < 0) trav_leaf_s<COUNT>(ray, acc, top_sp, BLOCK * 4, a.t_min, c, node, tc);
-        }
-        ++nr;
-        int id = c.code < 0 ? -1 : (int)((uint32_t)c.code & B200RT_CODE_ID_MASK);
-        a.ids[i] = id;
-        if (a.hits) {
-            B200rtHit out;
-            memset(&out, 0, sizeof out);
-            out.id = id;
-            if (id >= 0) {
-                HitRec h = make_hit(ray, acc, c);
-                float u, v;
-                hit_uv(h, acc, &u, &v);
-                out.t = h.t; out.p[0] = h.p.x; out.p[1] = h.p.y; out.p[2] = h.p.z;
-                out.n[0] = h.n.x; out.n[1] = h.n.y; out.n[2] = h.n.z;
-                out.u = u; out.v = v; out.front_face = h.front ? 1 : 0;
-            }
-            a.hits[i] = out;
+            const unsigned still = __ballot_sync(FULL, node != B200RT_TRAV_DONE);
+            if ((uint32_t)__popc(still) < (exhausted ? 1u : refill)) break;
         }
     }
     if (a.counters) {

@@ -66,6 +66,7 @@ struct Scratch {                     // per in-flight render: counters, events, 
     Counters* h_counters = nullptr;  // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t launch_stream = nullptr; bool launched = false;   // where the render in flight was enqueued (scene_destroy waits for it)
     float4* d_accum = nullptr; size_t accum_px = 0;
     uint8_t* d_rgb = nullptr; size_t rgb_bytes = 0;
     long long* d_fix = nullptr; size_t fix_px = 0;     // fixed-point sums of a launch whose tiles are split into sample chunks
@@ -80,6 +81,13 @@ struct Scratch {                     // per in-flight render: counters, events, 
 namespace {
 std::mutex g_scratch_mu;
 std::map<int, std::vector<Scratch*>> g_scratch_pool;
+// Scene arenas are pooled the same way: render_scene creates and destroys a scene per frame, and cudaFree is a
+// device-wide synchronisation (plus ~0.1 ms) that a 25 ms multi-GPU frame should not pay.  A destroyed scene's
+// arena waits here (at most ARENA_POOL_MAX per device) and is handed to the next scene that fits it without
+// wasting more than half of it.
+struct PooledArena { void* ptr; size_t bytes; };
+std::map<int, std::vector<PooledArena>> g_arena_pool;
+constexpr size_t ARENA_POOL_MAX = 4;
 }  // namespace
 
 struct B200rtScene {
@@ -89,6 +97,7 @@ struct B200rtScene {
     DeviceScene ds{};
     B200rtSceneInfo info{};
     std::vector<void*> allocs;
+    size_t arena_bytes = 0;       // capacity of allocs[0] (may exceed what this scene uses: pooled arenas are reused)
     std::mutex mu;
     std::map<void*, Scratch*> inflight;   // keyed by stream
     float box_pad = 0.f;          // how far every BVH box was grown
@@ -304,6 +313,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     a.plan = plan;
 
     scr->launches = 0;
+    scr->launch_stream = stream; scr->launched = true;
     CU(cudaEventRecord(scr->ev0, stream));
     CU(cudaMemsetAsync(scr->d_counters, 0, sizeof(Counters), stream));
     // The kernel stores every pixel of the tiles it renders; the buffer is cleared only when some pixels are outside them
@@ -377,6 +387,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
 
 int finish_render(Scratch* scr, cudaStream_t stream, cudaEvent_t end_event, B200rtStats* stats) {
     CU(cudaStreamSynchronize(stream));
+    scr->launched = false;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->rays = scr->h_counters->rays; stats->paths = scr->h_counters->paths;
@@ -594,9 +605,21 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     lap("lay out arena");
     uint8_t* dbase = nullptr;
     {
-        cudaError_t e = cudaMalloc(&dbase, arena.total);
+        size_t capacity = 0;
+        {   // a pooled arena of a destroyed scene, if one fits
+            std::lock_guard<std::mutex> gl(g_scratch_mu);
+            auto& pool = g_arena_pool[device];
+            for (size_t k = 0; k < pool.size(); ++k)
+                if (pool[k].bytes >= arena.total && pool[k].bytes <= 2 * arena.total + (1u << 20)) {
+                    dbase = static_cast<uint8_t*>(pool[k].ptr); capacity = pool[k].bytes;
+                    pool.erase(pool.begin() + k);
+                    break;
+                }
+        }
+        cudaError_t e = cudaSuccess;
+        if (!dbase) { e = cudaMalloc(&dbase, arena.total); capacity = arena.total; }
         if (e != cudaSuccess) return bail(fail(B200RT_ENOMEM, "scene arena (%zu B): %s", arena.total, cudaGetErrorString(e)));
-        sc->allocs.push_back(dbase);
+        sc->allocs.push_back(dbase); sc->arena_bytes = capacity;
         for (uint32_t i = 0; i < d->n_images; ++i) images[i].texels = reinterpret_cast<const uchar4*>(dbase + off_img[i]);
         e = arena.upload(dbase);
         if (e != cudaSuccess) return bail(fail(B200RT_ECUDA, "scene upload: %s", cudaGetErrorString(e)));
@@ -653,9 +676,22 @@ void b200rt_scene_destroy(B200rtScene* sc) {
     DeviceGuard guard(sc->device);
     {   // renders still in flight on this scene: wait, then return their scratch to the pool
         std::lock_guard<std::mutex> gl(g_scratch_mu);
-        for (auto& kv : sc->inflight) { if (kv.second->own_stream) cudaStreamSynchronize(kv.second->own_stream); g_scratch_pool[sc->device].push_back(kv.second); }
+        for (auto& kv : sc->inflight) {
+            // the arena goes back to a pool and may be overwritten by the next scene: nothing may still read it
+            if (kv.second->launched) cudaStreamSynchronize(kv.second->launch_stream);
+            kv.second->launched = false;
+            g_scratch_pool[sc->device].push_back(kv.second);
+        }
     }
-    if (!sc->allocs.empty()) cudaFree(sc->allocs[0]);   // one arena holds every scene array
+    if (!sc->allocs.empty()) {   // one arena holds every scene array: back to the pool (every render on it has been waited for above)
+        bool pooled = false;
+        {
+            std::lock_guard<std::mutex> gl(g_scratch_mu);
+            auto& pool = g_arena_pool[sc->device];
+            if (pool.size() < ARENA_POOL_MAX) { pool.push_back({sc->allocs[0], sc->arena_bytes}); pooled = true; }
+        }
+        if (!pooled) cudaFree(sc->allocs[0]);
+    }
     delete sc;
 }
 
@@ -1099,6 +1135,7 @@ int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, 
     HitArgs a{};
     a.scene = sc->ds; a.rays = d_rays.as<B200rtRay>(); a.n = n; a.t_min = t_min; a.t_max = t_max;
     a.ids = d_ids.as<int32_t>(); a.hits = hits ? d_hits.as<B200rtHit>() : nullptr; a.counters = d_ctr.as<Counters>();
+    a.next_ray = &d_ctr.as<Counters>()->diag[0];     // zeroed with the counters
     SmemPlan plan = make_plan(sc, 2);
     if (!plan.all_in_smem) { SmemPlan p1 = make_plan(sc, 1); if (p1.all_in_smem) plan = p1; }
     a.plan = plan;
@@ -1109,7 +1146,7 @@ int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, 
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, BLOCK, plan.bytes));
         if (bps < 1) return fail(B200RT_ECUDA, "closest_hit_kernel does not fit on an SM");
         size_t want = (n + BLOCK - 1) / BLOCK;
-        uint32_t grid = (uint32_t)std::min<size_t>(want, (size_t)sc->sm_count * bps * 4);
+        uint32_t grid = (uint32_t)std::min<size_t>(want, (size_t)sc->sm_count * bps);      // persistent: one wave of CTAs
         CU(cudaEventRecord(e0));
         kernel<<<grid, BLOCK, plan.bytes>>>(a);
         CU(cudaGetLastError());
