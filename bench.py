@@ -75,14 +75,54 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every 10 ms (the handle is opened in start(), before the timed region: an
+    8-GPU strong-scaled run times 5 x 25 ms and a `nvidia-smi -lms` child has not printed its first line by then).
+    Falls back to the `nvidia-smi -lms 100` loop of the profiling recipe when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.proc, self.lines = index, uuid, None, []
+        self.nvml, self.handle, self.samples, self.stop_flag, self.t = None, None, [], threading.Event(), None
+
+    def _open_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (f"GPU-{self.uuid}", str(self.uuid)):
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml, self.handle = pynvml, h
+        self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _poll_nvml(self):
+        n, h = self.nvml, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.010)
 
     def start(self):
+        try:
+            self._open_nvml()
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -96,6 +136,17 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            n = self.nvml
+            names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+            sm = sorted(s[0] for s in self.samples)
+            reasons = sorted({name for s in self.samples for name, bit in names if s[2] & bit})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max((s[1] for s in self.samples), default=None), "samples": len(sm), "reasons": reasons,
+                    "source": "NVML polled every 10 ms during the timed steps"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -117,7 +168,8 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 100 during the timed steps"}
 
 
 def algorithmic_ops_per_ray(node_visits, prim_tests, rays):
@@ -332,7 +384,7 @@ def main():
     fp32_peak = rt.fp32_peak(local_rank)   # lane-instr/s, measured live (FFMA chain)
 
     # ---- timed steps -----------------------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     sampler.start()
     step_ms, kernel_ms, rays, launches = [], [], 0, 0
     torch.cuda.synchronize()

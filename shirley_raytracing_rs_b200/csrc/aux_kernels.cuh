@@ -253,7 +253,9 @@ __global__ void scatter_kernel(const __grid_constant__ ScatterArgs a) {
         uint32_t s0 = rng.state;
         float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
         float3 albedo = sp.tex.need_perlin ? marble(sp.tex.perlin_scale, h.p, turb) : sp.tex.rgb;
-        ShadeOut so = shade_finish(ray, h, sp.m, albedo, rng, atten, emit);
+        ShadeOut so = shade_finish(ray, h, sp.m, albedo, rng);
+        if (so.has_emission) emit = emit + atten * so.emission;
+        if (so.has_mul) atten = atten * so.mul;
         out.ray.ox = so.o.x; out.ray.oy = so.o.y; out.ray.oz = so.o.z;
         out.ray.dx = so.d.x; out.ray.dy = so.d.y; out.ray.dz = so.d.z;
         out.attenuation[0] = atten.x; out.attenuation[1] = atten.y; out.attenuation[2] = atten.z;

@@ -298,7 +298,8 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     bool fast_ok = sc->box_pad >= 4.0f * 1.1920929e-7f * max_origin;
     bool fast = fast_ok && env_int("B200RT_FAST_SLAB", 1) != 0;
 
-    auto extra_for = [](int threads) { return (size_t)(threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)); };
+    // per warp: the fixed-point tile sums and the primary-ray ring; per thread: 7 words of path state (attenuation, emitted, pixel)
+    auto extra_for = [](int threads) { return (size_t)(threads / 32) * (96 * sizeof(long long) + RAYQ_FIELDS * RAYQ_SLOTS * sizeof(uint32_t)) + (size_t)threads * 7 * sizeof(float); };
     SmemPlan plan = make_plan(sc, 1, block_threads, extra_for(block_threads));
 #ifndef B200RT_DEV_BUILD
     // A deep tree (the device-built linear BVH can reach 40-50 levels) needs more stack per thread than
@@ -328,12 +329,17 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         const uint32_t warps_per_block = (uint32_t)block_threads / 32;
         const uint32_t my_tiles = (a.n_tiles + a.shard_count - 1) / a.shard_count;
         const uint32_t full_grid = (uint32_t)(sc->sm_count * blocks_per_sm);
-        // Work granularity: a warp takes whole tiles while the frame has >= ITEMS_PER_WARP of them per resident warp;
-        // below that each tile's samples are split into `chunks` ranges (at least MIN_CHUNK_SPP samples each) so the
+        // Work granularity: each tile's samples are split into `chunks` ranges (at least MIN_CHUNK_SPP samples each) so the
         // persistent grid stays balanced to the end of the launch.  B200RT_CHUNKS=n forces a split (1 = whole tiles).
-        const uint32_t ITEMS_PER_WARP = 80, MIN_CHUNK_SPP = 14;     // measured: profiles/ (chunk sweeps at 500, 63 and 50 spp)
-        uint64_t want_items = (uint64_t)ITEMS_PER_WARP * full_grid * warps_per_block;
-        uint32_t chunks = my_tiles ? (uint32_t)std::min<uint64_t>((want_items + my_tiles - 1) / my_tiles, std::max(1u, a.samples / MIN_CHUNK_SPP)) : 1u;
+        // Measured optimum (profiles/r02_experiments.md §2, §9): chunks ~ 1.7 sqrt(samples / tiles-per-resident-warp) for a scene
+        // in shared memory — 12 at 500 spp, 4 at 63, 3 at 32, 2 at 16 on the 1200x800 frame (10.6 tiles per warp), 1 on frames
+        // with >= 100 tiles per warp: a chunk's cost is draining the warp at its end (~ 1 / chunk size), its benefit the balance
+        // at the end of the launch (~ chunk size / (samples x tiles per warp)).  Scenes read through L1 pay more per item
+        // (neighbouring chunks no longer share a warp's L1 lines): factor 1.2, i.e. whole tiles on the config-4 frames.
+        const uint32_t MIN_CHUNK_SPP = 4;
+        const double tiles_per_warp = (double)my_tiles / ((double)full_grid * warps_per_block);
+        const double want = (plan.all_in_smem ? 1.7 : 1.2) * std::sqrt((double)a.samples / std::max(tiles_per_warp, 1e-6));
+        uint32_t chunks = my_tiles ? (uint32_t)std::min<double>(std::floor(want + 0.5), (double)std::max(1u, a.samples / MIN_CHUNK_SPP)) : 1u;
         if (int forced = env_int("B200RT_CHUNKS", 0)) chunks = (uint32_t)std::min<int64_t>(std::max(1, forced), (int64_t)a.samples);
         if ((uint64_t)my_tiles * chunks > 0xFFFFFFF0ull) chunks = 1;      // the 32-bit work counter
         a.chunks = chunks ? chunks : 1u;
@@ -661,6 +667,9 @@ int b200rt_scene_create(const B200rtSceneDesc* d, int device, B200rtScene** out)
     sc->box_pad = pad; sc->max_abs_coord = max_abs;
     sc->ds.n_nodes = (uint32_t)n_nodes; sc->ds.n_prims = d->n_prims; sc->ds.n_tex = d->n_textures; sc->ds.bvh_depth = bvh.depth;
     sc->ds.sky_kind = d->skybox.kind == B200RT_SKY_ABOVE ? B200RT_SKY_ABOVE : B200RT_SKY_FLAT;
+    sc->ds.has_emitters = 0;      // DiffuseLight / FairyLight present: ray_color's `emitted` accumulator is live (render kernel)
+    for (uint32_t i = 0; i < d->n_prims; ++i)
+        if (d->materials[i].kind == B200RT_MAT_DIFFUSE_LIGHT || d->materials[i].kind == B200RT_MAT_FAIRY_LIGHT) { sc->ds.has_emitters = 1; break; }
     bool flat = d->skybox.kind == B200RT_SKY_FLAT;
     sc->ds.sky_r = flat ? d->skybox.rgb[0] : 0.f; sc->ds.sky_g = flat ? d->skybox.rgb[1] : 0.f; sc->ds.sky_b = flat ? d->skybox.rgb[2] : 0.f;
     sc->info.n_prims = d->n_prims; sc->info.n_bvh_nodes = sc->ds.n_nodes; sc->info.bvh_depth = bvh.depth;

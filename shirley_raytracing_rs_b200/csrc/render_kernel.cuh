@@ -142,6 +142,18 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
     // per-warp queue of generated primary rays, SoA [RAYQ_FIELDS][RAYQ_SLOTS] behind the accumulators
     uint32_t* rayq = reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
                      + (threadIdx.x >> 5) * (RAYQ_FIELDS * RAYQ_SLOTS);
+    // Per-path state that is touched once per bounce — ray_color's attenuation and emitted accumulators (render.rs:24-25)
+    // and the path's tile pixel — lives in shared memory behind the ray queue, SoA [7][BLK]: seven registers fewer across
+    // the traversal loop.  `emitted` is only materialised for scenes with emissive materials (it is zero until the path ends
+    // otherwise).  Slot k of this thread = ps_s + k * BLK * 4 in the shared window.
+    const uint32_t ps_s = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<uint32_t*>(reinterpret_cast<long long*>(stack_base + a.plan.stack_depth * BLK) + (BLK / 32) * 96)
+                                                             + (BLK / 32) * (RAYQ_FIELDS * RAYQ_SLOTS) + threadIdx.x);
+    auto ps_ld = [&](int k) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ps_s + (uint32_t)k * BLK * 4u) : "memory"); return v; };
+    auto ps_st = [&](int k, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(ps_s + (uint32_t)k * BLK * 4u), "f"(v) : "memory"); };
+    auto ps_ld3 = [&](int k) { return f3(ps_ld(k), ps_ld(k + 1), ps_ld(k + 2)); };
+    auto ps_st3 = [&](int k, float3 v) { ps_st(k, v.x); ps_st(k + 1, v.y); ps_st(k + 2, v.z); };
+    constexpr int PS_ATTEN = 0, PS_EMIT = 3, PS_PIXEL = 6;
+    const bool has_emitters = a.scene.has_emitters != 0u;
     const float T_MIN = 0.001f;                      // render.rs:31
     const bool has_perlin = a.scene.perlin != nullptr;
     // (the Perlin tables stay in global memory behind L1: a shared-memory copy reached through generic loads measured 0.4 % slower)
@@ -182,12 +194,10 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         uint32_t q_head = 0, q_count = 0;  // the warp's ring of generated primary rays
         for (int k = lane; k < 96; k += 32) wacc[k] = 0;
         __syncwarp();
-        uint32_t pl = 0;                 // tile pixel (0..31) of the path this lane is tracing
         uint32_t nrays = 0, nexh = 0;   // nrays: warp total (same value in every lane), nexh: per lane
         TravCounters tc; tc.nodes = 0; tc.prims = 0;
         Rng rng; rng.state = 0; rng.inc = 1;
         RayF ray = make_ray_shade(f3(0, 0, 0), f3(0, 0, 1));
-        float3 atten = f3(1, 1, 1), emit = f3(0, 0, 0);
         uint32_t depth = 0;
         int node = B200RT_TRAV_DONE;
         const uint32_t stack_s = (uint32_t)__cvta_generic_to_shared(stack);
@@ -208,8 +218,10 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             ShadePrep sp_;
             sp_.tex.need_perlin = false; sp_.tex.perlin_idx = 0;
             h.p = f3(0.f, 0.f, 0.f);
-            if (fin && !hit) {
-                emit = emit + atten * background(a.scene, ray.d);
+            float3 radiance = f3(0.f, 0.f, 0.f);         // what the path adds to its pixel when it ends in this iteration
+            if (fin && !hit) {                           // render.rs:44-45: emitted + attenuation * background
+                const float3 bg = background(a.scene, ray.d);
+                radiance = has_emitters ? ps_ld3(PS_EMIT) + ps_ld3(PS_ATTEN) * bg : ps_ld3(PS_ATTEN) * bg;
                 done = true;
             }
             if (hit) {
@@ -221,14 +233,22 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 turb = coop_turbulence(perlin_tables, hit && sp_.tex.need_perlin, h.p, sp_.tex.perlin_idx);
             if (hit) {
                 float3 albedo = sp_.tex.need_perlin ? marble(sp_.tex.perlin_scale, h.p, turb) : sp_.tex.rgb;
-                ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng, atten, emit);
+                ShadeOut so = shade_finish(ray, h, sp_.m, albedo, rng);
+                if (so.has_emission) ps_st3(PS_EMIT, ps_ld3(PS_EMIT) + ps_ld3(PS_ATTEN) * so.emission);     // only scenes with emitters get here
                 done = !so.scattered;
                 if (!done) {
                     if (--depth == 0) { done = true; ++nexh; }
-                    else { ray.o = so.o; ray.d = so.d; setup = true; }
+                    else {
+                        ray.o = so.o; ray.d = so.d; setup = true;
+                        if (so.has_mul) ps_st3(PS_ATTEN, ps_ld3(PS_ATTEN) * so.mul);
+                    }
                 }
             }
-            if (done) { acc_add(wacc, pl, emit, sample_lim); depth = 0; }
+            if (done) {
+                if (has_emitters && hit) radiance = ps_ld3(PS_EMIT);      // ended on a light or ran out of depth: `emitted` so far
+                acc_add(wacc, __float_as_uint(ps_ld(PS_PIXEL)), radiance, sample_lim);
+                depth = 0;
+            }
 
             // ---- path regeneration: render_scanline's sample loop, render.rs:60-66 ----
             // Primary rays are generated 32 at a time into the warp's queue (all lanes busy: RNG
@@ -268,8 +288,10 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);
                 ray.o = f3(__uint_as_float(rayq[0 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[1 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[2 * RAYQ_SLOTS + slot]));
                 ray.d = f3(__uint_as_float(rayq[3 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[4 * RAYQ_SLOTS + slot]), __uint_as_float(rayq[5 * RAYQ_SLOTS + slot]));
-                rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot]; pl = rayq[8 * RAYQ_SLOTS + slot];
-                atten = f3(1, 1, 1); emit = f3(0, 0, 0);
+                rng.state = rayq[6 * RAYQ_SLOTS + slot]; rng.inc = rayq[7 * RAYQ_SLOTS + slot];
+                ps_st(PS_PIXEL, __uint_as_float(rayq[8 * RAYQ_SLOTS + slot]));
+                ps_st3(PS_ATTEN, f3(1, 1, 1));
+                if (has_emitters) ps_st3(PS_EMIT, f3(0, 0, 0));
                 depth = a.max_depth;
                 setup = depth != 0u;
             }

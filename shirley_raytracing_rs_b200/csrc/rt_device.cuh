@@ -65,6 +65,7 @@ struct DeviceScene {
     // traversal.  Entries are leaf-encoded (~((type << 28) | id)).  The reference keeps a
     // linear list beside its tree too (HitList for unbounded objects, scene/mod.rs:61-77).
     uint32_t n_top_prims; int top_prims[7];
+    uint32_t has_emitters;      // some material is a DiffuseLight / FairyLight (else `emitted` stays zero until a path ends)
 };
 
 // Camera constants, reduced on the host in f64 from camera/mod.rs:98-114:
@@ -671,9 +672,11 @@ __device__ __forceinline__ float3 background(const DeviceScene& s, float3 d) {
 }
 
 // Material::scatter + ::emitted (material_type.rs:50-79), in two halves around the (possibly
-// cooperative) texture evaluation.  `atten`/`emit` are ray_color's accumulators
-// (render.rs:24-25).  scattered == false ends the path (DiffuseLight).
-struct ShadeOut { float3 o, d; bool scattered; };
+// cooperative) texture evaluation.  ray_color's accumulators (render.rs:24-25) are updated by the caller from what
+// shade_finish returns — `emit += atten * emission` when has_emission, then `atten *= mul` when has_mul — so the
+// caller decides where they live (the render kernel keeps them in shared memory: they are touched once per bounce).
+// scattered == false ends the path (DiffuseLight).
+struct ShadeOut { float3 o, d; float3 mul, emission; bool scattered, has_mul, has_emission; };
 struct ShadePrep { MatRec m; TexResult tex; };
 
 template <class Acc>
@@ -686,10 +689,12 @@ __device__ __forceinline__ ShadePrep shade_prepare(const DeviceScene& s, const A
     return p;
 }
 
-__device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h, const MatRec& m, float3 a, Rng& rng, float3& atten, float3& emit) {
+__device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h, const MatRec& m, float3 a, Rng& rng) {
     ShadeOut out;
     out.o = h.p;
     out.scattered = true;
+    out.has_mul = false; out.has_emission = false;
+    out.mul = f3(1.f, 1.f, 1.f); out.emission = f3(0.f, 0.f, 0.f);
     if (m.kind == B200RT_MAT_DIELECTRIC) {                              // dielectric.rs:22-49
         float ir = m.m0.w;
         float ratio = h.front ? __fdividef(1.0f, ir) : ir;   // 2-ulp divide: IEEE `/` takes its slow path for ir = 1 (0 / 2 below)
@@ -715,29 +720,30 @@ __device__ __forceinline__ ShadeOut shade_finish(const RayF& r, const HitRec& h,
         return out;                                                     // attenuation = ones
     }
     if (m.kind == B200RT_MAT_DIFFUSE_LIGHT) {                           // lighting.rs:21-28
-        emit = emit + atten * a;
+        out.emission = a; out.has_emission = true;
         out.scattered = false;
         out.d = r.d;
         return out;
     }
     // Metal, Lambertian and FairyLight all start from a point in the unit ball
     float3 rs = random_in_unit_sphere(rng);
+    out.has_mul = true;
     if (m.kind == B200RT_MAT_METAL) {                                   // metal.rs:27-39: never absorbs, sampler drawn even for fuzz 0
         float3 ud = unit(r.d);
         float3 refl = ud - h.n * (2.0f * dot(ud, h.n));
         out.d = refl + rs * m.m0.w;
-        atten = atten * f3(m.m0.x, m.m0.y, m.m0.z);
+        out.mul = f3(m.m0.x, m.m0.y, m.m0.z);
         return out;
     }
     if (m.kind == B200RT_MAT_FAIRY_LIGHT) {                             // lighting.rs:59-66 then :43-57
         float scale = -dot(h.n, r.d) * rsqrtf(fmaf(r.d.z, r.d.z, fmaf(r.d.y, r.d.y, __fmul_rn(r.d.x, r.d.x))));
-        emit = emit + atten * (a * scale);
+        out.emission = a * scale; out.has_emission = true;
         a = unit(a);
     }
     float3 dir = h.n + unit(rs);                                        // lambertian.rs:23, math.rs:62-68
     if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = h.n;   // vec3.rs:130
     out.d = dir;
-    atten = atten * a;
+    out.mul = a;
     return out;
 }
 
