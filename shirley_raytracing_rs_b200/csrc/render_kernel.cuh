@@ -38,6 +38,7 @@ struct RenderArgs {
     uint32_t chunks;                            // work item = (tile, one of `chunks` contiguous sample ranges); > 1: sums go to `fix`
     long long* fix;                             // chunks > 1: per-pixel 2^-32 fixed-point sums [H][W][3] in global memory (finalize_kernel converts)
     uint32_t trav_threshold;                    // leave the traversal loop when fewer lanes than this still traverse
+    uint32_t regen_min;                         // hand out new paths only when at least this many lanes are free
     float4* accum;
     Counters* counters;
 };
@@ -49,14 +50,14 @@ template <> struct Stager<SmemAcc> {
     static __device__ __forceinline__ SmemAcc stage(const DeviceScene& s, const SmemPlan& plan, float4* smem, int** stack) {
         uint32_t n_nodes4 = s.n_nodes * 4, n_geom4 = s.n_prims * 2, n_mat4 = s.n_prims * 2, n_tex4 = s.n_tex * 2;
         float4* nodes = smem;
-        float4* geom = nodes + n_nodes4;
+        float4* geom = nodes + s.n_nodes * SMEM_NODE_QUADS;
         float4* mats = geom + n_geom4;
         float4* tex = mats + n_mat4;
         const float4* gn = reinterpret_cast<const float4*>(s.nodes);
         const float4* gg = reinterpret_cast<const float4*>(s.geom);
         const float4* gm = reinterpret_cast<const float4*>(s.mats);
         const float4* gt = reinterpret_cast<const float4*>(s.tex);
-        for (uint32_t i = threadIdx.x; i < n_nodes4; i += blockDim.x) nodes[i] = __ldg(gn + i);
+        for (uint32_t i = threadIdx.x; i < n_nodes4; i += blockDim.x) nodes[(i >> 2) * SMEM_NODE_QUADS + (i & 3u)] = __ldg(gn + i);
         for (uint32_t i = threadIdx.x; i < n_geom4; i += blockDim.x) geom[i] = __ldg(gg + i);
         for (uint32_t i = threadIdx.x; i < n_mat4; i += blockDim.x) mats[i] = __ldg(gm + i);
         for (uint32_t i = threadIdx.x; i < n_tex4; i += blockDim.x) tex[i] = __ldg(gt + i);
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
             // keying, jitter, lens rejection loop, Camera::pixel_ray) and handed out to the ~6 lanes
             // per iteration whose path ended; generating them on demand ran that code at 6 lanes.
             unsigned want_m = __ballot_sync(FULL, depth == 0u);
+            if ((uint32_t)__popc(want_m) < a.regen_min) want_m = 0u;      // too few free lanes: they wait an iteration
             const uint32_t want = (uint32_t)__popc(want_m);
             if (q_count < want && next_item < n_items) {           // warp-uniform
                 __syncwarp();
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
                 __syncwarp();
             }
             const uint32_t rank = (uint32_t)__popc(want_m & lt);
-            bool regen = depth == 0u && rank < q_count;
+            bool regen = depth == 0u && ((want_m >> lane) & 1u) && rank < q_count;
             if (COUNT) { d6 += __popc(__ballot_sync(FULL, regen)); d2 += __popc(__ballot_sync(FULL, depth == 0u && !regen)); }
             if (regen) {
                 uint32_t slot = (q_head + rank) & (RAYQ_SLOTS - 1);

@@ -84,9 +84,14 @@ struct DeviceCamera {
 // wavefronts per warp instead of up to 32 L1 tag lookups) or resident in global memory
 // behind the read-only path (GmemAcc), where the shared memory not used is left to the L1 cache.
 // ------------------------------------------------------------------------------------------
+// Staged nodes are padded to SMEM_NODE_QUADS x 16 B (80 B instead of 64): with a 64-byte stride the quad k of every node falls
+// into one of only two 16-byte bank groups (node parity), so the divergent LDS.128 of a quarter-warp collide; a stride of 5
+// quads walks all eight groups (measured +1.2 % on the bench frame; padding the 32-byte geometry records to 48 B the same
+// way measured 3 % slower).
+constexpr int SMEM_NODE_QUADS = 5;
 struct SmemAcc {
     const float4* nodes; const float4* geom; const float4* mats; const float4* tex;
-    __device__ __forceinline__ float4 node_q(int node, int k) const { return nodes[node * 4 + k]; }
+    __device__ __forceinline__ float4 node_q(int node, int k) const { return nodes[node * SMEM_NODE_QUADS + k]; }
     __device__ __forceinline__ float4 geom0(int id) const { return geom[id * 2]; }
     __device__ __forceinline__ float4 geom1(int id) const { return geom[id * 2 + 1]; }
     __device__ __forceinline__ MatRec mat(int id) const {
