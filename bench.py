@@ -60,7 +60,7 @@ sys.path.insert(0, ROOT)
 WIDTH, SPP, DEPTH, SCENE_SEED = 1200, 500, 50, 0xDEADBEEF
 WORKLOAD = "weekend_final_scene_1200x800_500spp_depth50"
 # ncu --set full of the C4 launches (scripts/profile_c4.py; profiles/r02_c4_metrics.md): bytes per 64-spp launch
-C4_NCU = {"lts_1e6": 328850676384, "dram_1e6": 438811136, "lts_1e5": 247191012224, "dram_1e5": 380317440}
+C4_NCU = {"lts_1e6": 267870144256, "dram_1e6": 172336384, "lts_1e5": 178832932832, "dram_1e5": 110871296}
 METRIC = "Mrays/s, Weekend final scene 1200x800 500spp (ms/frame in ms_per_step)"
 
 
@@ -675,7 +675,7 @@ def other_configs(rt, sharding, rank, world, local_rank, dev, stream, sptr, fp32
                                 "frac": rps * opr / (fp32_peak * world), "ops_per_ray": opr}}
             if not in_smem:
                 # The tree lives in global memory and is served mostly by L1 and L2 (ncu, profiles/r02_c4_metrics.md: L1 hit rate
-                # ~92 %, L2 ~80-87 %): algorithmic node + primitive bytes per ray x rays/s against the L2 read ceiling measured
+                # ~80-91 %, L2 ~83-88 %): algorithmic node + primitive bytes per ray x rays/s against the L2 read ceiling measured
                 # live (b200rt_read_peak over 48 MiB) and against the HBM figure of MEASURED_PEAKS.json.  `traffic` = what one
                 # 64-spp launch of this kernel moved at L2 (lts__t_bytes.sum) and at DRAM (dram__bytes_read + write), from ncu.
                 ncu = {"c4_1e6": {"lts_bytes": C4_NCU.get("lts_1e6"), "dram_bytes": C4_NCU.get("dram_1e6")}, "c4_1e5": {"lts_bytes": C4_NCU.get("lts_1e5"), "dram_bytes": C4_NCU.get("dram_1e5")}}
