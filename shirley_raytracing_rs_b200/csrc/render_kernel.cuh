@@ -111,14 +111,16 @@ __device__ __forceinline__ void acc_add(long long* acc, uint32_t pixel, float3 v
 
 // ------------------------------------------------------------------------------------------
 // K2: the persistent path-tracing kernel (render_scanline + ray_color, render.rs:17-70).
-// Grid = one CTA of BLK threads per SM; every warp pulls 8x4-pixel tiles from a global counter (bottom rows
-// first: the geometry-heavy tiles are scheduled before the cheap sky tiles) and works through the tile's
-// (pixel, sample) list with all 32 lanes.  ncu on the first, straight-loop design (render_variants.cuh) showed
-// 8.1 of 32 lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4, the marble texture
-// at 2.7 — so this kernel is organised around lane utilisation and instruction count:
-//  * one outer iteration = shade the lanes whose traversal finished -> hand new paths to lanes without one
-//    (from a per-warp ring of primary rays generated 32 at a time) -> ONE shared per-segment set-up for both
-//    groups (IEEE reciprocals, scene-spanning primitives tested up front) -> traverse;
+// Grid = one CTA of BLK threads per SM; every warp pulls work items — an 8x4-pixel tile and one of `chunks` ranges of
+// its samples — from a global counter (bottom rows first: the geometry-heavy tiles are scheduled before the cheap sky
+// tiles) and works through the item's (pixel, sample) list with all 32 lanes.  ncu on the first, straight-loop design
+// (round 1, git history) showed 8.1 of 32 lanes active per instruction — inner-node visits at 13 lanes, leaf tests at 4,
+// the marble texture at 2.7 — so this kernel is organised around lane utilisation, instruction count and registers:
+//  * one outer iteration = shade the lanes whose traversal finished -> hand new paths to the free lanes once at least
+//    `regen_min` of them are (from a per-warp ring of primary rays generated 32 at a time) -> ONE shared per-segment
+//    set-up for both groups (IEEE reciprocals, scene-spanning primitives tested up front) -> traverse;
+//  * state that is touched once per bounce (ray_color's attenuation and emitted accumulators, the path's pixel) lives in
+//    per-thread shared-memory slots, not in registers across the traversal loop;
 //  * while-while traversal with a resumable cursor: every lane runs inner-node visits until it holds a leaf,
 //    the warp tests the postponed leaves together, and leaves the loop as soon as fewer than `trav_threshold`
 //    lanes still traverse (finished lanes never idle until the slowest lane ends);
