@@ -301,3 +301,41 @@ def test_earth_scene_uses_the_reference_asset(rt, po, gpu_required):
     rmse = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))
     floor = rmse(a / spp, b / spp)
     assert 0.5 * (rmse(g[..., :3] / spp, a / spp) + rmse(g[..., :3] / spp, b / spp)) < 1.25 * floor + 1e-4
+
+
+def test_concurrent_renders_from_host_threads(rt, weekend, gpu_required):
+    """SURVEY §8b threading: a scene handle is immutable after create and several host threads may render from it at
+    once (rayon workers share `&Frame`, src/main.rs:118-125), each call on its own stream and scratch; scenes may be
+    created and destroyed meanwhile.  Every concurrent result equals the sequential one bit for bit."""
+    import threading
+    cam = rt.default_camera(150)
+    seeds = list(range(40, 48))
+    want = {s: rt.render(weekend, cam, samples=6, seed=s)[0] for s in seeds}
+    got, errors = {}, []
+
+    def worker(s):
+        try:
+            for _ in range(3):
+                got[s] = rt.render(weekend, cam, samples=6, seed=s)[0]
+        except Exception as e:                                   # noqa: BLE001 - reported below
+            errors.append((s, repr(e)))
+
+    def churn():
+        try:
+            for k in range(6):
+                other = rt.Scene.named("random", seed=100 + k)
+                a, _ = rt.render(other, cam, samples=2, seed=1)
+                assert np.isfinite(a).all()
+                del other
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(("churn", repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in seeds] + [threading.Thread(target=churn)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert all(not t.is_alive() for t in threads)
+    for s in seeds:
+        assert np.array_equal(got[s], want[s]), s
