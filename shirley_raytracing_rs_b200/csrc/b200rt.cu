@@ -250,8 +250,13 @@ void put_scratch(B200rtScene* sc, void* stream_key) {
     sc->inflight.erase(it);
 }
 
-template <class K> int set_smem(K kernel, uint32_t bytes) {
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+// The attribute belongs to the kernel function, not to a launch: host threads rendering different scenes at once would
+// lower it under each other's feet if it were set to each launch's own size ("too many resources requested for launch",
+// found by tests/test_gpu_scale.py::test_concurrent_renders_from_host_threads).  It is therefore always raised to the device's
+// opt-in maximum — the same value from every thread; the carve-out still follows the bytes each launch asks for.
+template <class K> int set_smem(K kernel, const B200rtScene* sc, uint32_t bytes) {
+    if (bytes > sc->smem_optin) return fail(B200RT_ECUDA, "kernel needs %u B of shared memory, the device offers %zu", bytes, (size_t)sc->smem_optin);
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_optin));
     return B200RT_OK;
 }
 
@@ -326,7 +331,7 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
     if (!a.accumulate && !covers_frame) CU(cudaMemsetAsync(d_accum, 0, (size_t)W * H * sizeof(float4), stream));
     int blocks_per_sm = 0;
     auto go = [&](auto kernel) -> int {
-        int rc = set_smem(kernel, plan.bytes); if (rc) return rc;
+        int rc = set_smem(kernel, sc, plan.bytes); if (rc) return rc;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, block_threads, plan.bytes));
         if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path-tracing kernel does not fit on an SM (smem %u B, %d threads)", plan.bytes, block_threads);
         const uint32_t warps_per_block = (uint32_t)block_threads / 32;
@@ -1153,7 +1158,7 @@ int b200rt_closest_hit(const B200rtScene* csc, const B200rtRay* rays, size_t n, 
     a.plan = plan;
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     auto go = [&](auto kernel) -> int {
-        int r2 = set_smem(kernel, plan.bytes); if (r2) return r2;
+        int r2 = set_smem(kernel, sc, plan.bytes); if (r2) return r2;
         int bps = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, BLOCK, plan.bytes));
         if (bps < 1) return fail(B200RT_ECUDA, "closest_hit_kernel does not fit on an SM");

@@ -322,8 +322,10 @@ def test_concurrent_renders_from_host_threads(rt, weekend, gpu_required):
 
     def churn():
         try:
-            for k in range(6):
-                other = rt.Scene.named("random", seed=100 + k)
+            for k in range(12):
+                # scenes of different sizes: their launches ask for different amounts of shared memory (the per-function
+                # MaxDynamicSharedMemorySize attribute once raced between such threads)
+                other = rt.Scene.named(("cornell", "random", "perlin")[k % 3], seed=100 + k)
                 a, _ = rt.render(other, cam, samples=2, seed=1)
                 assert np.isfinite(a).all()
                 del other
