@@ -1,0 +1,89 @@
+"""Randomised scenes through the reference's builder API: the BVH closest-hit of the device (either builder, scenes staged in
+shared memory or read through L1) against the brute-force f32 restatement of its arithmetic over every object in id order
+(oracle/gpu_f32.hpp) — ids, t, normals bit for bit — on scenes the named factories never produce: a handful of primitives,
+all three rect orientations, boxes thinner than the box padding, concentric and coincident spheres, huge and tiny radii,
+primitives far from the origin.  Closest hits must not depend on the tree, so every seed also checks the other builder."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+INF = float("inf")
+
+
+def _random_scene(rt, rng, n, spread):
+    b = rt.SceneBuilder()
+    if rng.random() < 0.3:
+        b.set_skybox(rt.SkyBox.None_)
+    solid = lambda: rt.TextureLoader.solid(*rng.uniform(0.05, 0.95, 3))
+    mats = [lambda: rt.Lambertian(solid()),
+            lambda: rt.Lambertian(rt.TextureLoader.checker(float(rng.uniform(0.5, 9)), solid(), rt.TextureLoader.noise(float(rng.uniform(0.5, 4))))),
+            lambda: rt.Metal(tuple(rng.uniform(0.3, 1, 3)), float(rng.uniform(0, 0.6))),
+            lambda: rt.Dielectric(float(rng.choice([1.0, 1.33, 1.5, 2.4]))),
+            lambda: rt.DiffuseLight(solid()), lambda: rt.FairyLight(solid())]
+    centres = rng.uniform(-spread, spread, size=(max(n, 1), 3))
+    for k in range(n):
+        c = centres[k if rng.random() > 0.15 else rng.integers(0, max(k, 1))]          # some coincident centres
+        kind = rng.integers(0, 6)
+        if kind <= 2:
+            r = float(rng.choice([rng.uniform(0.05, 0.3), rng.uniform(0.5, 3.0), 1e-3, 0.25 * spread]))
+            geom = rt.Sphere(tuple(c), r)
+        elif kind <= 4:
+            a0, a1 = sorted(rng.uniform(-1, 1, 2) * rng.choice([0.2, 2.0, spread]) + c[0])
+            b0, b1 = sorted(rng.uniform(-1, 1, 2) * rng.choice([0.2, 2.0, spread]) + c[1])
+            geom = (rt.xy_rect, rt.yz_rect, rt.xz_rect)[rng.integers(0, 3)](float(a0), float(a1), float(b0), float(b1), float(c[2]))
+        else:
+            ext = rng.choice([1e-5, 0.01, 0.5, 2.0], size=3) * rng.uniform(0.5, 1.5, 3)        # incl. slabs thinner than the box padding
+            geom = rt.RectBox(tuple(c), tuple(c + ext))
+        b.add(geom, mats[rng.integers(0, len(mats))]())
+    return b.finalize()
+
+
+def _rays(rng, n, spread):
+    o = rng.uniform(-1.5 * spread, 1.5 * spread, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d[: n // 8] = np.eye(3)[rng.integers(0, 3, n // 8)] * rng.choice([-1.0, 1.0], size=(n // 8, 1))   # axis-parallel: 1/d = inf on two axes
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, d], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scenes_ids_bit_exact(rt, po, gpu_required, monkeypatch, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([0, 1, 2, 3, 5, 17, 64, 300, 2500]))
+    spread = float(rng.choice([3.0, 30.0, 2000.0]))
+    s = _random_scene(rt, rng, n, spread)
+    rays = _rays(rng, 60_000, spread)
+    want = po.closest_hit_gpu32(s.desc, rays, 0.001, INF)
+    for builder in ("sah", "lbvh"):
+        monkeypatch.setenv("B200RT_BUILDER", builder)
+        s2 = rt.Scene.from_json(s.to_json()) if builder == "lbvh" else s       # a fresh handle: the tree is built at upload
+        ids, hits, st = rt.closest_hit(s2, rays, 0.001, INF)
+        assert np.array_equal(ids, want["id"]), (seed, n, spread, builder, int((ids != want["id"]).sum()))
+        hit = ids >= 0
+        assert np.array_equal(hits["t"][hit], want["t"][hit]) and np.array_equal(hits["n"][hit], want["n"][hit]), (seed, builder)
+        assert np.array_equal(hits["front_face"][hit], want["front_face"][hit])
+    monkeypatch.delenv("B200RT_BUILDER")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_scenes_render_is_finite_and_deterministic(rt, gpu_required, monkeypatch, seed):
+    """The render kernel on the same kind of scene: finite sums, the same image whatever the work split and the builder,
+    sample counts and path statistics consistent."""
+    rng = np.random.default_rng(2000 + seed)
+    n = int(rng.choice([1, 4, 40, 400]))
+    s = _random_scene(rt, rng, n, 6.0)
+    cam = rt.camera((14, 5, 9), (0, 0, 0), vfov=45, aperture=0.05, width=176, aspect_ratio=(16, 9), focus_length=12.0)
+    base, st = rt.render(s, cam, samples=9, max_depth=12, seed=seed)
+    assert np.isfinite(base).all() and np.all(base[..., 3] == 9) and np.all(base[..., :3] >= 0)
+    assert st.paths == cam.image_width * cam.image_height * 9 and st.rays >= st.paths
+    for var, val in (("B200RT_CHUNKS", "3"), ("B200RT_REGEN_MIN", "2"), ("B200RT_BUILDER", "lbvh")):
+        monkeypatch.setenv(var, val)
+        s2 = rt.Scene.from_json(s.to_json()) if var == "B200RT_BUILDER" else s
+        got, st2 = rt.render(s2, cam, samples=9, max_depth=12, seed=seed)
+        monkeypatch.delenv(var)
+        if var == "B200RT_BUILDER":
+            # Perlin tables are re-seeded identically by from_json (same perlin_seed), so the image is the same too
+            assert np.array_equal(got, base), (seed, var)
+        else:
+            assert np.array_equal(got, base), (seed, var)
+        assert st2.rays == st.rays
