@@ -102,3 +102,25 @@ def test_random_scenes_render_is_finite_and_deterministic(rt, gpu_required, monk
         else:
             assert np.array_equal(got, base), (seed, var)
         assert st2.rays == st.rays
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_scenes_render_rmse_vs_oracle(rt, po, gpu_required, seed):
+    """Level 3 on scenes with every material and texture kind mixed (lights, fairy lights, dielectrics of several indices,
+    checker-of-noise): RMSE(GPU mean, oracle mean) within 1.25x the oracle-vs-oracle floor of two independent runs, mean
+    brightness and segments per sample in agreement."""
+    rng = np.random.default_rng(3000 + seed)
+    s = _random_scene(rt, rng, int(rng.choice([12, 40, 120])), 5.0)
+    cam = rt.camera((13, 4, 8), (0, 0, 0), vfov=40, aperture=0.02, width=80, aspect_ratio=(16, 9), focus_length=14.0)
+    spp = 400
+    o = po.OracleScene(s.desc)
+    o1, st1 = o.render(cam, spp, max_depth=20, seed=11)
+    o2, _ = o.render(cam, spp, max_depth=20, seed=22)
+    g, st = rt.render(s, cam, samples=spp, max_depth=20, seed=33)
+    m1, m2, mg = o1 / spp, o2 / spp, g[..., :3].astype(np.float64) / spp
+    rmse = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))
+    floor = rmse(m1, m2)
+    got = 0.5 * (rmse(mg, m1) + rmse(mg, m2))
+    assert got < 1.25 * floor + 1e-4, (seed, got, floor)
+    assert abs(mg.mean() - 0.5 * (m1.mean() + m2.mean())) < 0.03 * max(m1.mean(), 1e-3) + 4 * floor / np.sqrt(mg.size / 3)
+    assert abs(st.rays / st.paths - st1.rays / st1.paths) < 0.02 * st1.rays / st1.paths
