@@ -335,22 +335,52 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, block_threads, plan.bytes));
         if (blocks_per_sm < 1) return fail(B200RT_ECUDA, "path-tracing kernel does not fit on an SM (smem %u B, %d threads)", plan.bytes, block_threads);
         const uint32_t warps_per_block = (uint32_t)block_threads / 32;
-        const uint32_t my_tiles = (a.n_tiles + a.shard_count - 1) / a.shard_count;
+        const uint32_t my_tiles = a.n_tiles > a.shard_index ? (a.n_tiles - a.shard_index + a.shard_count - 1) / a.shard_count : 0u;   // tiles t with t % shard_count == shard_index
         const uint32_t full_grid = (uint32_t)(sc->sm_count * blocks_per_sm);
-        // Work granularity: each tile's samples are split into `chunks` ranges (at least MIN_CHUNK_SPP samples each) so the
-        // persistent grid stays balanced to the end of the launch.  B200RT_CHUNKS=n forces a split (1 = whole tiles).
-        // Measured optimum (profiles/r02_experiments.md §2, §9): chunks ~ 1.7 sqrt(samples / tiles-per-resident-warp) for a scene
-        // in shared memory — 12 at 500 spp, 4 at 63, 3 at 32, 2 at 16 on the 1200x800 frame (10.6 tiles per warp), 1 on frames
-        // with >= 100 tiles per warp: a chunk's cost is draining the warp at its end (~ 1 / chunk size), its benefit the balance
-        // at the end of the launch (~ chunk size / (samples x tiles per warp)).  Scenes read through L1 pay more per item
-        // (neighbouring chunks no longer share a warp's L1 lines): factor 1.2, i.e. whole tiles on the config-4 frames.
-        const uint32_t MIN_CHUNK_SPP = 4;
+        // Work granularity (profiles/r02_experiments.md §2, §9, §17).  A tile's samples are split into sample ranges that SHRINK:
+        // the launch ends when the last item ends, so the last items must be small (a whole-tile item of the 1200x800 frame is
+        // ~1 ms: 5 % of a 63-spp launch, which is what one of 8 GPUs renders), while big items are cheaper per sample (a warp
+        // drains once per item).  Guided schedule: each range takes 70 % of what is left — at most `cap` samples, so that even
+        // the biggest ranges give every resident warp two items on frames with fewer tiles than warps — until the rest is
+        // below ~1.5x the target size of the last range, 0.2 % of a warp's share of the launch (2 % for scenes read through L1,
+        // where every extra item costs L1 locality and atomics: whole tiles on the config-4 frames).  Items are handed out
+        // range by range, bottom rows first within each.  Measured against uniform ranges: +2.9 % at 500 spp, +5.8 % at 63 spp,
+        // +4.7 % at 16 spp on the bench frame.  B200RT_CHUNKS=n forces n ranges (geometric, last / first = B200RT_TAPER %).
+        const uint32_t S = a.samples;
         const double tiles_per_warp = (double)my_tiles / ((double)full_grid * warps_per_block);
-        const double want = (plan.all_in_smem ? 1.7 : 1.2) * std::sqrt((double)a.samples / std::max(tiles_per_warp, 1e-6));
-        uint32_t chunks = my_tiles ? (uint32_t)std::min<double>(std::floor(want + 0.5), (double)std::max(1u, a.samples / MIN_CHUNK_SPP)) : 1u;
-        if (int forced = env_int("B200RT_CHUNKS", 0)) chunks = (uint32_t)std::min<int64_t>(std::max(1, forced), (int64_t)a.samples);
-        if ((uint64_t)my_tiles * chunks > 0xFFFFFFF0ull) chunks = 1;      // the 32-bit work counter
-        a.chunks = chunks ? chunks : 1u;
+        const double share = std::max((double)S * tiles_per_warp, 1e-9);                  // samples x tiles a resident warp renders
+        const double last_target = std::max(1.0, (plan.all_in_smem ? 0.002 : 0.02) * share);
+        const double cap = std::max(1.0, 0.5 * share);
+        uint32_t sizes[MAX_CHUNKS]; uint32_t C = 0;
+        const int forced = env_int("B200RT_CHUNKS", 0);
+        if (forced > 0) {
+            C = (uint32_t)std::min<int64_t>(std::min<int64_t>(forced, MAX_CHUNKS), S);
+            const double w = std::min(100, std::max(1, std::abs(env_int("B200RT_TAPER", 3)))) / 100.0;
+            const double r = C > 1 ? std::pow(w, 1.0 / (C - 1)) : 1.0;
+            uint32_t prev = 0;
+            for (uint32_t k = 1; k <= C; ++k) {
+                const double F = r < 0.999999 ? (1.0 - std::pow(r, (double)k)) / (1.0 - std::pow(r, (double)C)) : (double)k / C;
+                uint32_t b = k == C ? S : (uint32_t)std::llround(F * S);
+                b = std::min(std::max(b, prev + 1u), S - (C - k));            // every range non-empty
+                sizes[k - 1] = b - prev; prev = b;
+            }
+        } else {
+            uint32_t rem = S;
+            double cap_now = cap;
+            while (rem > 0) {
+                uint32_t s = (uint32_t)std::llround(std::min(cap_now, 0.7 * rem));
+                s = std::min(std::max(s, 1u), rem);
+                if (rem <= (uint32_t)std::ceil(1.5 * last_target) || C + 1 == MAX_CHUNKS) s = (C + 1 == MAX_CHUNKS || rem <= cap_now * 1.5) ? rem : s;
+                sizes[C++] = s; rem -= s;
+                if (C + 8 >= MAX_CHUNKS) cap_now = std::max(cap_now, (double)rem / 6.0);      // running out of table entries: bigger ranges
+            }
+        }
+        if (C == 0) { sizes[0] = S; C = 1; }
+        if ((uint64_t)my_tiles * C > 0xFFFFFFF0ull) { sizes[0] = S; C = 1; }      // the 32-bit work counter
+        a.chunks = C;
+        a.my_tiles = my_tiles ? my_tiles : 1u;
+        a.chunk_begin[0] = 0;
+        for (uint32_t k = 0; k < MAX_CHUNKS; ++k) a.chunk_begin[k + 1] = k < C ? a.chunk_begin[k] + sizes[k] : S;
         a.fix = nullptr;
         if (a.chunks > 1u) {
             const size_t px = (size_t)W * H;

@@ -11,6 +11,7 @@ namespace b200rt {
 constexpr int BLOCK = 256;          // threads per CTA of the parity-hook kernels (K1); the render kernel's CTA size is its BLK template argument (768 by default)
 constexpr size_t LBVH_AUTO_MIN = 262144;   // primitives from which scene_create builds the tree on the device
 constexpr int TILE_W = 8, TILE_H = 4;   // one warp renders an 8x4 pixel tile, one lane per pixel
+constexpr uint32_t MAX_CHUNKS = 64;     // sample ranges per tile
 
 struct SmemPlan {
     uint32_t all_in_smem;           // 1: nodes + geom + mats + tex all staged (SmemAcc)
@@ -36,6 +37,11 @@ struct RenderArgs {
     uint32_t shard_count, shard_index;
     uint32_t accumulate;
     uint32_t chunks;                            // work item = (tile, one of `chunks` contiguous sample ranges); > 1: sums go to `fix`
+    // Items are handed out chunk by chunk (all tiles' first ranges, then all second ones, ...) and the ranges SHRINK
+    // (chunk_begin[k] .. chunk_begin[k + 1]): big items while the grid is full, small ones at the end of the launch, where the
+    // last items to finish decide how long the other SMs idle.  my_tiles = this shard's tiles.
+    uint32_t my_tiles;
+    uint32_t chunk_begin[MAX_CHUNKS + 1];
     long long* fix;                             // chunks > 1: per-pixel 2^-32 fixed-point sums [H][W][3] in global memory (finalize_kernel converts)
     uint32_t trav_threshold;                    // leave the traversal loop when fewer lanes than this still traverse
     uint32_t regen_min;                         // hand out new paths only when at least this many lanes are free
@@ -174,15 +180,14 @@ __global__ void __launch_bounds__(BLK, MINB) path_trace_kernel_v2(const __grid_c
         unsigned int j = 0;
         if (lane == 0) j = atomicAdd(&a.counters->tile_counter, 1u);
         j = __shfl_sync(FULL, j, 0);
-        // Work item j = (tile j / chunks, sample range j % chunks): a tile's samples are split over several warps when the
+        // Work item j = (sample range j / my_tiles, tile j % my_tiles): a tile's samples are split over several warps when the
         // frame has too few tiles to balance the grid (1200x800 at 500 spp is 10.5 whole tiles per warp: the kernel ran 18 %
-        // below its rate on frames with 4x the tiles).  Bottom rows first either way.
-        const uint32_t chunk = a.chunks > 1u ? j % a.chunks : 0u;
-        unsigned long long t64 = (unsigned long long)(a.chunks > 1u ? j / a.chunks : j) * a.shard_count + a.shard_index;
-        if (t64 >= a.n_tiles) break;
-        const uint32_t s_begin = (uint32_t)((unsigned long long)a.samples * chunk / a.chunks);
-        const uint32_t s_count = (uint32_t)((unsigned long long)a.samples * (chunk + 1u) / a.chunks) - s_begin;
-        uint32_t t = (uint32_t)t64;
+        // below its rate on frames with 4x the tiles).  Bottom rows first within every range.
+        const uint32_t chunk = j / a.my_tiles;
+        if (chunk >= a.chunks) break;
+        const uint32_t t = (j - chunk * a.my_tiles) * a.shard_count + a.shard_index;
+        const uint32_t s_begin = a.chunk_begin[chunk];
+        const uint32_t s_count = a.chunk_begin[chunk + 1u] - s_begin;
         uint32_t ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         const uint32_t px0 = tx * TILE_W, py0 = (a.tile_row0 + ty) * TILE_H;
         const uint32_t my_px = px0 + (lane & (TILE_W - 1)), my_py = py0 + (lane >> 3);
