@@ -541,7 +541,7 @@ def main():
                     "frac": achieved / fp32_peak if fp32_peak else None,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
                     # profiles/): the scene is staged in shared memory, HBM is idle
-                    "traffic": 23568600, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one 500-spp launch (ncu --set full, profiles/r02_ncu_metrics.md, last column): 23.18 MB read + 0.39 MB written; the 15 MB accumulation buffer and the 23 MB fixed-point sums of the chunked tiles stay in L2",
+                    "traffic": 23805200, "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one 500-spp launch (ncu --set full, profiles/r02_ncu_metrics.md, last column): 23.18 MB read + 0.63 MB written; the 15 MB accumulation buffer and the 23 MB fixed-point sums of the chunked tiles stay in L2",
                     "kernel": "path_trace_kernel_v2", "kernel_ms": float(np.mean(kernel_ms)),
                     "ops_per_ray": ops_per_ray, "node_visits_per_ray": c_nodes / c_rays, "prim_tests_per_ray": c_prims / c_rays,
                     "segments_per_sample": c_rays / c_paths,
