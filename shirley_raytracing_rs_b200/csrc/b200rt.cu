@@ -340,8 +340,8 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         // Work granularity (profiles/r02_experiments.md §2, §9, §17).  A tile's samples are split into sample ranges that SHRINK:
         // the launch ends when the last item ends, so the last items must be small (a whole-tile item of the 1200x800 frame is
         // ~1 ms: 5 % of a 63-spp launch, which is what one of 8 GPUs renders), while big items are cheaper per sample (a warp
-        // drains once per item).  Guided schedule: each range takes 70 % of what is left — at most `cap` samples, so that even
-        // the biggest ranges give every resident warp two items on frames with fewer tiles than warps — until the rest is
+        // drains once per item).  Guided schedule: each range takes 70 % of what is left — at most `cap` samples, 7 % of a warp's
+        // share of the launch, so that frames with few tiles per warp (tile shards, small images) still balance — until the rest is
         // below ~1.5x the target size of the last range, 0.2 % of a warp's share of the launch (2 % for scenes read through L1,
         // where every extra item costs L1 locality and atomics: whole tiles on the config-4 frames).  Items are handed out
         // range by range, bottom rows first within each.  Measured against uniform ranges: +2.9 % at 500 spp, +5.8 % at 63 spp,
@@ -350,7 +350,9 @@ int launch_render(B200rtScene* sc, const B200rtCamera* cam, const B200rtRenderPa
         const double tiles_per_warp = (double)my_tiles / ((double)full_grid * warps_per_block);
         const double share = std::max((double)S * tiles_per_warp, 1e-9);                  // samples x tiles a resident warp renders
         const double last_target = std::max(1.0, (plan.all_in_smem ? 0.002 : 0.02) * share);
-        const double cap = std::max(1.0, 0.5 * share);
+        // no item above ~7 % of a warp's share (a heavy tile costs ~3x the average one) — but not below 8 samples (256 paths) either
+        // when that share is small (tiny frames): an item drains the warp once whatever its size
+        const double cap = std::max(std::max(1.0, 0.07 * share), std::min(8.0, 0.5 * share));
         uint32_t sizes[MAX_CHUNKS]; uint32_t C = 0;
         const int forced = env_int("B200RT_CHUNKS", 0);
         if (forced > 0) {
